@@ -1,0 +1,167 @@
+/*
+ * silent_b200.h -- C ABI of libsilent_b200.so: pySILEnT's slam_recognition filter pipeline on B200 (sm_100a).
+ *
+ * The reference (SimLeek/pySILEnT) has no native code: its hot path is Python that builds a TensorFlow-1 graph plus a
+ * scipy pyramid builder. Each entry point below cites the reference interface it replaces (paths relative to
+ * /root/reference/slam_recognition); INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 (SILENT_OK) or a negative silent_status; silent_last_error() returns a thread-local
+ *    message for the last failure on the calling thread.
+ *  - the caller owns every buffer. Pointers named *_dev are device pointers on the current CUDA device, *_host are
+ *    host pointers. Nothing is allocated inside a call except by silent_plan_create / silent_plan_reserve (plan-owned
+ *    tap tables, workspace and staging buffers, freed by silent_plan_destroy).
+ *  - every launch is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) unless the
+ *    function name ends in _host, which synchronises before returning.
+ *  - tensors are NHWC float32, contiguous: [levels, h, w, C] exactly as the reference feeds its placeholder
+ *    (recognition_testing.py:62,130). Filters are HWIO float32 [k, k, Cin, Cout] (constant_convolutions/).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point returns SILENT_E_CUDA.
+ */
+#ifndef SILENT_B200_H
+#define SILENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SILENT_ABI_VERSION 1
+
+typedef enum silent_status {
+    SILENT_OK = 0,
+    SILENT_E_INVAL = -1,    /* bad argument (null pointer, non-positive size, scale <= 1, ...) */
+    SILENT_E_SHAPE = -2,    /* shape / channel count / filter size not supported by this entry point */
+    SILENT_E_CAPACITY = -3, /* plan workspace or caller buffer too small */
+    SILENT_E_CUDA = -4,     /* CUDA runtime error (message has the cudaError string) */
+    SILENT_E_STRUCTURE = -5 /* weights lack the structure the fused stack needs; use the per-operator calls */
+} silent_status;
+
+typedef enum silent_dtype { SILENT_U8 = 0, SILENT_F32 = 1 } silent_dtype;
+
+typedef void *silent_stream; /* cudaStream_t */
+typedef struct silent_plan silent_plan;
+
+/* Geometry of the pyramid build: the arguments of zoom.from_image(image, num_colors, center_dimensions, scale)
+ * (util/zoom/from_image.py:10-14) plus the frame shape/dtype the reference reads from the ndarray. */
+typedef struct silent_params {
+    int32_t frame_h, frame_w, frame_c; /* input frames are [H, W, frame_c], channel-interleaved */
+    int32_t num_colors;                /* channels 0..num_colors-1 go into the pyramid (from_image.py:54) */
+    int32_t center_w, center_h;        /* center_dimensions, (w, h) order as the reference passes it (from_image.py:44) */
+    double scale;                      /* zoom_ratio > 1 (from_image.py:38) */
+    int32_t frame_dtype;               /* silent_dtype of the frames: SILENT_U8 (camera) or SILENT_F32 */
+    int32_t reserved;
+} silent_params;
+
+/* Weights and constants of the fused stack = the graph LineEndDisplayer.compile builds (recognition_testing.py:69-77).
+ * All filters HWIO float32. */
+typedef struct silent_stack_weights {
+    float rgc[3 * 3 * 3 * 3];    /* midget_rgc(2),            filters/rgc.py:9-11 */
+    float rgby[3 * 3 * 3 * 3];   /* rgby_3(2),                filters/rgby.py:9-10 */
+    float stripe[3 * 3 * 3 * 3]; /* rgb_2d_stripe_tensors(),  filters/orientation.py:19-22 */
+    float blur[7 * 7 * 3 * 3];   /* blur_tensor(2, 7),        filters/orientation.py:20,31 */
+    float end[3 * 3 * 3 * 3];    /* rgb_2d_end_tensors(),     recognition_testing.py:29 */
+    float regulation_value;      /* 1.0,   filters/orientation.py:33 */
+    float regulation_root;       /* 0.1,   filters/orientation.py:33 */
+    float clip_max;              /* 255,   recognition_testing.py:74 */
+    int32_t border;              /* 2,     recognition_testing.py:75 */
+} silent_stack_weights;
+
+int silent_abi_version(void);
+const char *silent_last_error(void);
+/* Number of CUDA devices visible, or a negative status. */
+int silent_device_count(void);
+
+/* ---- plan ------------------------------------------------------------------------------------------------------ */
+
+/* Replaces the per-call geometry code of image_to_zoom_tensor (from_image.py:43-51): level count, crop bounds and the
+ * order-5 spline tap tables of scipy.ndimage.zoom(prefilter=False), computed once in float64 on the host. */
+int silent_plan_create(const silent_params *params, silent_plan **out_plan);
+void silent_plan_destroy(silent_plan *plan);
+/* Pre-size the plan-owned workspace / pinned staging buffers for up to max_batch frames (needed by *_host calls and
+ * silent_pipeline_run). May be called again with a larger batch. */
+int silent_plan_reserve(silent_plan *plan, int max_batch);
+
+int silent_plan_levels(const silent_plan *plan);                 /* num_scales, from_image.py:45-46 */
+int silent_plan_level_hw(const silent_plan *plan, int *h, int *w); /* reversed center_dimensions */
+/* Crop [y0,y1) x [x0,x1) of `level` in the frame (from_image.py:49-51) and the rows/cols actually written (:61-62). */
+int silent_plan_level_info(const silent_plan *plan, int level, int *y0, int *y1, int *x0, int *x1, int *valid_h,
+                           int *valid_w);
+/* Test hook: copy the host tap tables of one level. idx_y/w_y: [h][6], idx_x/w_x: [w][6]; idx[.][0] < 0 marks an
+ * output row/column that is defined as 0. */
+int silent_plan_level_tables(const silent_plan *plan, int level, int32_t *idx_y, float *w_y, int32_t *idx_x,
+                             float *w_x);
+/* Algorithmic HBM bytes of one frame through silent_pipeline_run: union crop read + two output
+ * tensors; feature points excluded. */
+int64_t silent_plan_algorithmic_bytes(const silent_plan *plan);
+
+/* ---- per-operator entry points ----------------------------------------------------------------------------------- */
+
+/* zoom.from_image (util/zoom/from_image.py:10-69) for a batch: frames_dev [batch, H, W, frame_c] of params.frame_dtype
+ * -> pyramid_dev [batch * L, h, w, num_colors] float32. Rows/columns the reference leaves uninitialised are 0. */
+int silent_pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev,
+                         silent_stream stream);
+
+/* tf.nn.conv2d(x, filter, [1,1,1,1], 'SAME') as used by apply_filter (util/apply_filter.py:4-7), optionally followed by
+ * tf.maximum(., [0]) (post = 1; filters/rgc.py:13-16, rgby.py:11-12, orientation.py:24-29) and tf.clip_by_value(., 0,
+ * clip_max) (post = 2; recognition_testing.py:73-74). cin, cout <= 8; k odd, <= 7. */
+int silent_conv2d(const float *x_dev, int n, int h, int w, int cin, const float *filter_hwio_dev, int k, int cout,
+                  int post, float clip_max, float *out_dev, silent_stream stream);
+
+/* regulate_tensor(input, blur, regulation_value, regulation_root) (util/regulator/gaussian_regulator_tensor.py:10-36):
+ * out = x * (value / pow(min(conv2d(x, blur), 1), root)). blur is [k, k, c, c]. */
+int silent_regulate(const float *x_dev, int n, int h, int w, int c, const float *blur_hwio_dev, int k, float value,
+                    float root, float *out_dev, silent_stream stream);
+
+/* pad_inwards(tensor, [[0,0],[top,bottom],[left,right],[0,0]]) (util/selection/isolate_rectangle.py:19-23). */
+int silent_pad_inwards(const float *x_dev, int n, int h, int w, int c, int top, int bottom, int left, int right,
+                       float *out_dev, silent_stream stream);
+
+/* get_value_from_color (util/color/get_value.py:6-12): [n,h,w,c] -> [n,h,w,1]. */
+int silent_value_from_color(const float *x_dev, int n, int h, int w, int c, float *out_dev, silent_stream stream);
+
+/* Workspace bytes for the two selection calls below. */
+size_t silent_selection_workspace_bytes(int n, int h, int w);
+
+/* max_value_indices_region(color, region_shape, value) (util/selection/top_value_points.py:32-45): writes int64 rows
+ * (level, y, x, 0) in row-major order to points_dev[capacity][4] and the TOTAL number of qualifying pixels to
+ * *count_dev (it can exceed capacity; only the first `capacity` rows are written). value_dev is [n,h,w,1]. */
+int silent_max_value_indices_region(const float *value_dev, int n, int h, int w, int region_h, int region_w,
+                                    int64_t *points_dev, int64_t capacity, int64_t *count_dev, void *workspace_dev,
+                                    size_t workspace_bytes, silent_stream stream);
+
+/* top_value_points(color, top_percent, value) (util/selection/top_value_points.py:8-29). */
+int silent_top_value_points(const float *color_dev, const float *value_dev, int n, int h, int w, int c,
+                            double top_percent, float *out_dev, void *workspace_dev, size_t workspace_bytes,
+                            silent_stream stream);
+
+/* ---- fused path ---------------------------------------------------------------------------------------------------- */
+
+/* S1-S7 of LineEndDisplayer.compile (recognition_testing.py:69-77) in one kernel: pyramid_dev [n,h,w,3] ->
+ * orient_dev (orient_tensor), line_end_dev (padded_line_end_tensor), both [n,h,w,3], and gray_dev [n,h,w,1]
+ * (gray_line_end_tensor). Any output pointer may be NULL to skip its store. Returns SILENT_E_STRUCTURE when the weights
+ * are not (stripe: identical input-channel slices; blur: all slices identical), which the reference's generators
+ * always produce. */
+int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const silent_stack_weights *weights_host,
+                       float *orient_dev, float *line_end_dev, float *gray_dev, silent_stream stream);
+
+/* The whole hot path for a batch resident in HBM: frames -> pyramid -> S1-S7 -> feature points (S8, region =
+ * (h/2, w/2), recognition_testing.py:40,90-91). Uses the plan workspace (silent_plan_reserve(batch) first).
+ * Outputs as in silent_stack_fused / silent_max_value_indices_region; pyramid_dev may be NULL (plan scratch is used). */
+int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
+                        float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
+                        int64_t capacity, int64_t *count_dev, silent_stream stream);
+
+/* Same, with HOST buffers on both sides: the drop-in for LineEndDisplayer.callback (recognition_testing.py:136-144):
+ * frames_host [batch,H,W,frame_c] -> orient_host, line_end_host [batch*L,h,w,3], points_host [capacity][4], *count_host.
+ * Copies go through plan-owned pinned staging buffers; synchronises `stream` before returning. Output pointers may be
+ * NULL to skip the corresponding device->host copy. */
+int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_host,
+                             int batch, float *orient_host, float *line_end_host, int64_t *points_host,
+                             int64_t capacity, int64_t *count_host, silent_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SILENT_B200_H */

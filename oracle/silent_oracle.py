@@ -38,7 +38,8 @@ def bspline5(x):
     m2 = (x >= 1) & (x < 2)
     out = np.where(m2, (51 + 75 * x - 210 * x2 + 150 * x2 * x - 45 * x2 * x2 + 5 * x2 * x2 * x) / 120.0, out)
     m3 = (x >= 2) & (x < 3)
-    out = np.where(m3, (3 - x) ** 5 / 120.0, out)
+    t = 3 - x
+    out = np.where(m3, t * t * t * t * t / 120.0, out)
     return out
 
 

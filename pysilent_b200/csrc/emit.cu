@@ -1,0 +1,275 @@
+// K3: feature-point emit = max_value_indices_region (reference util/selection/top_value_points.py:32-45) and the
+// top-percent mask top_value_points (:8-29).
+//
+// max_value_indices_region: max-pool with ksize = whole level and stride = region (SAME) -> NN-upsample -> value >= up
+// -> tf.where. Here: (1) per-window maxima (NaN-propagating), (2) per-row hit counts, (3) exclusive scan over rows,
+// (4) ordered warp-ballot compaction, so the int64 rows (level, y, x, 0) come out in tf.where's row-major order.
+#include "plan.h"
+
+namespace silent {
+
+struct PoolGeom {
+    int oh, ow;          // pooled grid
+    int pt, pl;          // SAME pad before
+    float sy, sx;        // float32(in / out) of the NN upsample, in = pooled, out = level
+};
+
+static PoolGeom pool_geometry(int h, int w, int region_h, int region_w)
+{
+    PoolGeom g;
+    g.oh = ceil_div(h, region_h);
+    g.ow = ceil_div(w, region_w);
+    int total_h = (g.oh - 1) * region_h + h - h, total_w = (g.ow - 1) * region_w + w - w;   // ksize = (h, w)
+    g.pt = (total_h > 0 ? total_h : 0) / 2;
+    g.pl = (total_w > 0 ? total_w : 0) / 2;
+    g.sy = (float)((double)g.oh / (double)h);
+    g.sx = (float)((double)g.ow / (double)w);
+    return g;
+}
+
+__device__ __forceinline__ int nearest_src(int dst, float scale, int n_in)
+{
+    const int src = (int)floorf((float)dst * scale);
+    return src < n_in - 1 ? src : n_in - 1;
+}
+
+constexpr float kNegInf = -INFINITY;
+
+// grid (oh*ow, n); one CTA reduces one window of one level.
+__global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict__ value, int h, int w, int region_h,
+                                                         int region_w, PoolGeom g, float *__restrict__ pooled)
+{
+    const int win = blockIdx.x, n = blockIdx.y;
+    const int i = win / g.ow, j = win % g.ow;
+    int ya = i * region_h - g.pt, yb = ya + h, xa = j * region_w - g.pl, xb = xa + w;
+    ya = max(ya, 0), xa = max(xa, 0), yb = min(yb, h), xb = min(xb, w);
+    const int ww = xb - xa, count = (yb - ya) * ww;
+    const float *v = value + (size_t)n * h * w;
+    float best = kNegInf;
+    int seen_nan = 0;
+    for (int t = threadIdx.x; t < count; t += blockDim.x) {
+        const float f = __ldg(v + (size_t)(ya + t / ww) * w + xa + t % ww);
+        if (f != f) seen_nan = 1;
+        else if (f > best) best = f;
+    }
+    __shared__ float s_best[8];
+    __shared__ int s_nan[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));   // no NaN reaches here
+        seen_nan |= __shfl_xor_sync(0xffffffffu, seen_nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best, s_nan[threadIdx.x >> 5] = seen_nan;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = fmaxf(best, s_best[k]), seen_nan |= s_nan[k];
+        pooled[(size_t)n * g.oh * g.ow + win] = seen_nan ? __int_as_float(0x7fc00000) : best;
+    }
+}
+
+// One warp per row (level, y). Pass 0 counts hits, pass 1 writes them at row_offset in x order.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) emit_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
+                                                        const float *__restrict__ pooled, int *__restrict__ row_count,
+                                                        const long long *__restrict__ row_offset,
+                                                        long long *__restrict__ points, long long capacity)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int n = row / h, y = row % h;
+    const float *v = value + (size_t)row * w;
+    const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
+    long long base = WRITE ? row_offset[row] : 0;
+    int total = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        bool hit = false;
+        if (x < w) hit = __ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow));
+        const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+        if (WRITE) {
+            if (hit) {
+                const long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+                if (slot < capacity) {
+                    longlong2 a = make_longlong2(n, y), b = make_longlong2(x, 0);
+                    reinterpret_cast<longlong2 *>(points)[slot * 2] = a;
+                    reinterpret_cast<longlong2 *>(points)[slot * 2 + 1] = b;
+                }
+            }
+            base += __popc(ballot);
+        } else {
+            total += __popc(ballot);
+        }
+    }
+    if (!WRITE && lane == 0) row_count[row] = total;
+}
+
+// Single-CTA exclusive scan of the per-row counts (rows = levels * h, at most a few hundred thousand).
+__global__ void __launch_bounds__(1024) scan_rows_kernel(const int *__restrict__ row_count, int rows,
+                                                         long long *__restrict__ row_offset, long long *__restrict__ total)
+{
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < rows; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long mine = i < rows ? row_count[i] : 0;
+        long long incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long wsum = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(0xffffffffu, wsum, o);
+                if (lane >= o) wsum += up;
+            }
+            s_warp[lane] = wsum;
+        }
+        __syncthreads();
+        const long long before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - mine;
+        if (i < rows) row_offset[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + mine;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// top_value_points: per-level threshold (1-p)*max + p*min with min = -1 * max(-v); NaN in a level poisons its threshold.
+__global__ void __launch_bounds__(256) level_threshold_kernel(const float *__restrict__ value, int hw, float keep_max,
+                                                              float keep_min, float *__restrict__ thr)
+{
+    const float *v = value + (size_t)blockIdx.x * hw;
+    float mx = kNegInf, mneg = kNegInf;
+    int seen_nan = 0;
+    for (int t = threadIdx.x; t < hw; t += blockDim.x) {
+        const float f = __ldg(v + t);
+        if (f != f) seen_nan = 1;
+        else {
+            if (f > mx) mx = f;
+            if (-f > mneg) mneg = -f;
+        }
+    }
+    __shared__ float s_mx[8], s_mn[8];
+    __shared__ int s_nan[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mneg = fmaxf(mneg, __shfl_xor_sync(0xffffffffu, mneg, o));
+        seen_nan |= __shfl_xor_sync(0xffffffffu, seen_nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx, s_mn[threadIdx.x >> 5] = mneg, s_nan[threadIdx.x >> 5] = seen_nan;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+            mx = fmaxf(mx, s_mx[k]), mneg = fmaxf(mneg, s_mn[k]), seen_nan |= s_nan[k];
+        const float mn = -1.0f * mneg;
+        thr[blockIdx.x] = seen_nan ? __int_as_float(0x7fc00000) : keep_max * mx + keep_min * mn;
+    }
+}
+
+__global__ void apply_threshold_kernel(const float *__restrict__ color, const float *__restrict__ value,
+                                       const float *__restrict__ thr, size_t total, int hw, int c, float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i / c;
+    const float keep = value[pix] >= thr[pix / hw] ? 1.0f : 0.0f;
+    out[i] = color[i] * keep;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t selection_bytes(int n, int h, int w)
+{
+    const size_t rows = (size_t)n * h;
+    (void)w;
+    return align_up((size_t)n * 4096 * sizeof(float), 256) + align_up(rows * sizeof(int), 256) +
+           align_up(rows * sizeof(long long), 256) + 256;
+}
+
+int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
+                             int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
+                             cudaStream_t stream)
+{
+    if (!value || !count || !workspace || (!points && capacity > 0))
+        return fail(SILENT_E_INVAL, "silent_max_value_indices_region: null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(SILENT_E_INVAL, "silent_max_value_indices_region: bad shape");
+    if (region_h <= 0 || region_w <= 0) return fail(SILENT_E_INVAL, "region shape must be positive");
+    if (capacity < 0) return fail(SILENT_E_INVAL, "capacity must be >= 0");
+    if (n > 65535) return fail(SILENT_E_SHAPE, "at most 65535 levels per call");
+    const PoolGeom g = pool_geometry(h, w, region_h, region_w);
+    if (g.oh * g.ow > 4096) return fail(SILENT_E_SHAPE, "too many regions per level (%d x %d)", g.oh, g.ow);
+    if (workspace_bytes < selection_bytes(n, h, w))
+        return fail(SILENT_E_CAPACITY, "selection workspace too small: %zu < %zu", workspace_bytes,
+                    selection_bytes(n, h, w));
+    const int rows = n * h;
+    char *ws = (char *)workspace;
+    float *pooled = (float *)ws;
+    ws += align_up((size_t)n * 4096 * sizeof(float), 256);
+    int *row_count = (int *)ws;
+    ws += align_up((size_t)rows * sizeof(int), 256);
+    long long *row_offset = (long long *)ws;
+
+    window_max_kernel<<<dim3(g.oh * g.ow, n), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
+    SILENT_LAUNCH_CHECK("window_max_kernel");
+    const int warps_per_block = 8;
+    const unsigned blocks = (unsigned)ceil_div(rows, warps_per_block);
+    emit_rows_kernel<false><<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_count, nullptr, nullptr, 0);
+    SILENT_LAUNCH_CHECK("emit_rows_kernel<count>");
+    scan_rows_kernel<<<1, 1024, 0, stream>>>(row_count, rows, row_offset, (long long *)count);
+    SILENT_LAUNCH_CHECK("scan_rows_kernel");
+    if (capacity > 0) {
+        emit_rows_kernel<true><<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, nullptr, row_offset,
+                                                           (long long *)points, (long long)capacity);
+        SILENT_LAUNCH_CHECK("emit_rows_kernel<write>");
+    }
+    return SILENT_OK;
+}
+
+}  // namespace silent
+
+using namespace silent;
+
+extern "C" {
+
+size_t silent_selection_workspace_bytes(int n, int h, int w)
+{
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return selection_bytes(n, h, w);
+}
+
+int silent_max_value_indices_region(const float *value_dev, int n, int h, int w, int region_h, int region_w,
+                                    int64_t *points_dev, int64_t capacity, int64_t *count_dev, void *workspace_dev,
+                                    size_t workspace_bytes, silent_stream stream)
+{
+    return max_value_indices_region(value_dev, n, h, w, region_h, region_w, points_dev, capacity, count_dev,
+                                    workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int silent_top_value_points(const float *color_dev, const float *value_dev, int n, int h, int w, int c,
+                            double top_percent, float *out_dev, void *workspace_dev, size_t workspace_bytes,
+                            silent_stream stream)
+{
+    if (!color_dev || !value_dev || !out_dev || !workspace_dev)
+        return fail(SILENT_E_INVAL, "silent_top_value_points: null argument");
+    if (n <= 0 || h <= 0 || w <= 0 || c <= 0) return fail(SILENT_E_INVAL, "silent_top_value_points: bad shape");
+    if (workspace_bytes < (size_t)n * sizeof(float)) return fail(SILENT_E_CAPACITY, "selection workspace too small");
+    float *thr = (float *)workspace_dev;
+    // (1.0 - top_percent) and top_percent are Python floats converted to float32 constants by TF (top_value_points.py:22)
+    const float keep_max = (float)(1.0 - top_percent), keep_min = (float)top_percent;
+    cudaStream_t s = (cudaStream_t)stream;
+    level_threshold_kernel<<<n, 256, 0, s>>>(value_dev, h * w, keep_max, keep_min, thr);
+    SILENT_LAUNCH_CHECK("level_threshold_kernel");
+    const size_t total = (size_t)n * h * w * c;
+    apply_threshold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(color_dev, value_dev, thr, total, h * w, c,
+                                                                            out_dev);
+    SILENT_LAUNCH_CHECK("apply_threshold_kernel");
+    return SILENT_OK;
+}
+
+}  // extern "C"

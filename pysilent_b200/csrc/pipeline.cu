@@ -1,0 +1,171 @@
+// The whole hot path behind one call: frames -> pyramid (K1) -> fused stack (K2) -> feature points (K3).
+// silent_pipeline_run works on buffers resident in HBM; silent_pipeline_run_host is the drop-in for
+// LineEndDisplayer.callback (reference recognition_testing.py:136-144) with host buffers on both sides.
+#include <cstring>
+
+#include "plan.h"
+
+namespace silent {
+int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
+int stack_fused(const float *pyr, int n, int h, int w, const silent_stack_weights *W, float *orient, float *line_end,
+                float *gray, cudaStream_t stream);
+int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
+                             int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
+
+static void release(Workspace &ws)
+{
+    cudaFree(ws.d_frames);
+    cudaFree(ws.d_pyramid);
+    cudaFree(ws.d_orient);
+    cudaFree(ws.d_line_end);
+    cudaFree(ws.d_gray);
+    cudaFree(ws.d_select);
+    cudaFree(ws.d_points);
+    cudaFree(ws.d_count);
+    cudaFreeHost(ws.h_frames);
+    cudaFreeHost(ws.h_orient);
+    cudaFreeHost(ws.h_line_end);
+    cudaFreeHost(ws.h_points);
+    cudaFreeHost(ws.h_count);
+    ws = Workspace();
+}
+
+// Page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory) can be copied asynchronously in place;
+// pageable memory is staged through the plan's pinned mirrors.
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+static size_t frame_bytes(const silent_plan *plan)
+{
+    const silent_params &p = plan->params;
+    return (size_t)p.frame_h * p.frame_w * p.frame_c * (p.frame_dtype == SILENT_U8 ? 1 : 4);
+}
+
+}  // namespace silent
+
+using namespace silent;
+
+silent_plan::~silent_plan()
+{
+    release(ws);
+    if (d_tables) cudaFree(d_tables);
+}
+
+extern "C" {
+
+int silent_plan_reserve(silent_plan *plan, int max_batch)
+{
+    if (!plan) return fail(SILENT_E_INVAL, "null plan");
+    if (max_batch <= 0) return fail(SILENT_E_INVAL, "max_batch must be positive");
+    if (!plan->on_device && plan->levels > 0)
+        return fail(SILENT_E_CUDA, "plan was created without a CUDA device; no CPU fallback exists");
+    Workspace &ws = plan->ws;
+    if (ws.batch >= max_batch) return SILENT_OK;
+    release(ws);
+    const size_t n = (size_t)max_batch * (plan->levels > 0 ? plan->levels : 1);
+    const size_t level_elems = (size_t)plan->h * plan->w;
+    const size_t tensor_bytes = n * level_elems * 3 * sizeof(float);
+    const size_t pyr_bytes = n * level_elems * plan->params.num_colors * sizeof(float);
+    ws.select_bytes = silent_selection_workspace_bytes((int)n, plan->h, plan->w);
+    ws.points_capacity = (int64_t)n * 64;
+    SILENT_CUDA(cudaMalloc(&ws.d_frames, frame_bytes(plan) * max_batch));
+    SILENT_CUDA(cudaMalloc(&ws.d_pyramid, pyr_bytes));
+    SILENT_CUDA(cudaMalloc(&ws.d_orient, tensor_bytes));
+    SILENT_CUDA(cudaMalloc(&ws.d_line_end, tensor_bytes));
+    SILENT_CUDA(cudaMalloc(&ws.d_gray, n * level_elems * sizeof(float)));
+    SILENT_CUDA(cudaMalloc(&ws.d_select, ws.select_bytes));
+    SILENT_CUDA(cudaMalloc(&ws.d_points, ws.points_capacity * 4 * sizeof(int64_t)));
+    SILENT_CUDA(cudaMalloc(&ws.d_count, sizeof(int64_t)));
+    SILENT_CUDA(cudaMallocHost(&ws.h_frames, frame_bytes(plan) * max_batch));
+    SILENT_CUDA(cudaMallocHost(&ws.h_orient, tensor_bytes));
+    SILENT_CUDA(cudaMallocHost(&ws.h_line_end, tensor_bytes));
+    SILENT_CUDA(cudaMallocHost(&ws.h_points, ws.points_capacity * 4 * sizeof(int64_t)));
+    SILENT_CUDA(cudaMallocHost(&ws.h_count, sizeof(int64_t)));
+    ws.batch = max_batch;
+    return SILENT_OK;
+}
+
+int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
+                        float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
+                        int64_t capacity, int64_t *count_dev, silent_stream stream)
+{
+    if (!plan || !weights_host || !frames_dev) return fail(SILENT_E_INVAL, "silent_pipeline_run: null argument");
+    if (batch <= 0) return fail(SILENT_E_INVAL, "batch must be positive");
+    if (plan->params.num_colors != 3) return fail(SILENT_E_SHAPE, "the fused stack needs num_colors == 3");
+    if (plan->levels == 0) return fail(SILENT_E_SHAPE, "frame is not larger than the pyramid centre: 0 levels");
+    if ((plan->h % 2) || (plan->w % 2))
+        return fail(SILENT_E_SHAPE, "Ambiguous dimension: region shape (h/2, w/2) must be integral (h=%d, w=%d)", plan->h,
+                    plan->w);
+    Workspace &ws = plan->ws;
+    if (ws.batch < batch)
+        return fail(SILENT_E_CAPACITY, "plan workspace holds %d frames, need %d: call silent_plan_reserve", ws.batch, batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = batch * plan->levels;
+    float *pyr = pyramid_dev ? pyramid_dev : ws.d_pyramid;
+    int rc = pyramid_build(plan, frames_dev, batch, pyr, s);
+    if (rc != SILENT_OK) return rc;
+    rc = stack_fused(pyr, n, plan->h, plan->w, weights_host, orient_dev, line_end_dev, ws.d_gray, s);
+    if (rc != SILENT_OK) return rc;
+    if (count_dev)
+        rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
+                                      count_dev, ws.d_select, ws.select_bytes, s);
+    return rc;
+}
+
+int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_host,
+                             int batch, float *orient_host, float *line_end_host, int64_t *points_host,
+                             int64_t capacity, int64_t *count_host, silent_stream stream)
+{
+    if (!plan || !weights_host || !frames_host) return fail(SILENT_E_INVAL, "silent_pipeline_run_host: null argument");
+    if (batch <= 0) return fail(SILENT_E_INVAL, "batch must be positive");
+    if (capacity < 0) return fail(SILENT_E_INVAL, "capacity must be >= 0");
+    int rc = silent_plan_reserve(plan, batch);
+    if (rc != SILENT_OK) return rc;
+    Workspace &ws = plan->ws;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t in_bytes = frame_bytes(plan) * batch;
+    const size_t n = (size_t)batch * plan->levels;
+    const size_t tensor_bytes = n * plan->h * plan->w * 3 * sizeof(float);
+
+    const void *src = frames_host;
+    if (!is_pinned(frames_host)) {
+        std::memcpy(ws.h_frames, frames_host, in_bytes);
+        src = ws.h_frames;
+    }
+    SILENT_CUDA(cudaMemcpyAsync(ws.d_frames, src, in_bytes, cudaMemcpyHostToDevice, s));
+    const int64_t cap = capacity < ws.points_capacity ? capacity : ws.points_capacity;
+    rc = silent_pipeline_run(plan, weights_host, ws.d_frames, batch, nullptr, orient_host ? ws.d_orient : nullptr,
+                             line_end_host ? ws.d_line_end : nullptr, ws.d_points, cap, ws.d_count, stream);
+    if (rc != SILENT_OK) return rc;
+    const bool orient_direct = orient_host && is_pinned(orient_host);
+    const bool line_end_direct = line_end_host && is_pinned(line_end_host);
+    if (orient_host)
+        SILENT_CUDA(cudaMemcpyAsync(orient_direct ? orient_host : ws.h_orient, ws.d_orient, tensor_bytes,
+                                    cudaMemcpyDeviceToHost, s));
+    if (line_end_host)
+        SILENT_CUDA(cudaMemcpyAsync(line_end_direct ? line_end_host : ws.h_line_end, ws.d_line_end, tensor_bytes,
+                                    cudaMemcpyDeviceToHost, s));
+    SILENT_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    if (points_host && cap > 0)
+        SILENT_CUDA(cudaMemcpyAsync(ws.h_points, ws.d_points, cap * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SILENT_CUDA(cudaStreamSynchronize(s));
+    if (orient_host && !orient_direct) std::memcpy(orient_host, ws.h_orient, tensor_bytes);
+    if (line_end_host && !line_end_direct) std::memcpy(line_end_host, ws.h_line_end, tensor_bytes);
+    const int64_t total = *ws.h_count;
+    if (count_host) *count_host = total;
+    if (points_host && cap > 0) {
+        const int64_t rows = total < cap ? total : cap;
+        std::memcpy(points_host, ws.h_points, rows * 4 * sizeof(int64_t));
+    }
+    return SILENT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Internal definition of the opaque silent_plan.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace silent {
+
+struct LevelInfo {
+    int y0, y1, x0, x1;     // crop of this level in the frame (from_image.py:49-51)
+    int valid_h, valid_w;   // rows / cols the reference actually writes (from_image.py:61-62)
+};
+
+// Plan-owned device scratch, sized by silent_plan_reserve(max_batch).
+struct Workspace {
+    int batch = 0;
+    void *d_frames = nullptr;      // [B,H,W,FC] staging for *_host calls
+    float *d_pyramid = nullptr;    // [B*L,h,w,C]
+    float *d_orient = nullptr;     // [B*L,h,w,3] staging for *_host calls
+    float *d_line_end = nullptr;
+    float *d_gray = nullptr;       // [B*L,h,w]
+    void *d_select = nullptr;      // selection workspace
+    size_t select_bytes = 0;
+    int64_t *d_points = nullptr;   // [points_capacity][4]
+    int64_t points_capacity = 0;
+    int64_t *d_count = nullptr;
+    void *h_frames = nullptr;      // pinned mirrors
+    float *h_orient = nullptr;
+    float *h_line_end = nullptr;
+    int64_t *h_points = nullptr;
+    int64_t *h_count = nullptr;
+};
+
+}  // namespace silent
+
+struct silent_plan {
+    silent_params params;
+    int levels = 0, h = 0, w = 0;
+    int union_h = 0, union_w = 0;
+    bool on_device = false;
+    std::vector<silent::LevelInfo> info;
+    std::vector<int32_t> idx_y, idx_x;   // [L][h|w][6], absolute frame row / column, idx[.][0] = -1 => sample is 0
+    std::vector<float> w_y, w_x;
+    void *d_tables = nullptr;
+    int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
+    float *d_w_y = nullptr, *d_w_x = nullptr;
+    silent::Workspace ws;
+
+    ~silent_plan();
+};

@@ -1,0 +1,172 @@
+"""``LineEndPipeline``: the fused hot path behind the interface of the reference's ``LineEndDisplayer``.
+
+Reference: ``slam_recognition/recognition_testing.py:20-144``. ``compile()`` there builds, per pyramid shape, the graph
+rgc -> rgby -> orientation -> end filter -> relu/clip -> border mask -> value -> region-max feature points; ``run()``
+feeds one pyramid and fetches the result tensors; ``callback(frame, cam_id)`` is what the camera thread calls.
+Here the graph is three CUDA kernels (pyramid, fused stack, point emit) behind ``libsilent_b200.so``; "compiling" is
+building a plan (tap tables) per frame shape, cached like the reference caches its session per shape (``:108-118``).
+"""
+import collections
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, _ops
+from .constant_convolutions.center_surround import midget_rgc, rgby_3
+from .constant_convolutions.edge_orientation_detector import rgb_2d_stripe_tensors
+from .constant_convolutions.gaussian_blur.gaussian_blur import blur_tensor
+from .constant_convolutions.oriented_end_detector import rgb_2d_end_tensors
+from .util.zoom.from_image import get_plan
+
+LineEndResult = collections.namedtuple("LineEndResult", "orient padded_line_end gray points")
+LineEndResult.__doc__ = """orient: ``orient_tensor`` [N,h,w,3]; padded_line_end: ``padded_line_end_tensor`` [N,h,w,3];
+gray: ``gray_line_end_tensor`` [N,h,w,1] (or None); points: int64 [K,4] rows (level, y, x, 0) (``top_percent_points``)."""
+
+
+class LineEndPipeline:
+    """Drop-in for the compute half of ``LineEndDisplayer`` (camera / window handling is out of scope).
+
+    Constructor keywords follow ``PyramidDisplayer.__init__`` (``pyramid_displayer.py:22``): ``output_size`` is
+    ``(w, h)`` of every pyramid level, ``zoom_ratio`` the scale between levels.
+    """
+
+    def __init__(self, n_dimensions=2, output_size=(288, 192), output_colors=3, zoom_ratio=math.e ** .5, device=None):
+        self.output_size = tuple(output_size)
+        self.output_colors = output_colors
+        self.zoom_ratio = zoom_ratio
+        self.simplex_end_stop = rgb_2d_end_tensors()                                   # recognition_testing.py:29
+        self.region_shape = [1, self.output_size[1] / 2.0, self.output_size[0] / 2.0, self.output_colors]   # :40
+        self.blur_size = 7
+        self.device = torch.device(device) if device is not None else None
+        self._weights = None
+        self._weights_key = None
+
+    # -- weights ------------------------------------------------------------------------------------------------------
+    def filters(self):
+        """HWIO float64 filters in graph order (recognition_testing.py:69-73)."""
+        return dict(rgc=midget_rgc(2), rgby=rgby_3(2), stripe=rgb_2d_stripe_tensors(),
+                    blur=blur_tensor(2, lengths=self.blur_size), end=np.asarray(self.simplex_end_stop))
+
+    def stack_weights(self):
+        end = np.ascontiguousarray(np.asarray(self.simplex_end_stop), dtype=np.float32)
+        key = (end.tobytes(), self.blur_size)
+        if self._weights is None or key != self._weights_key:
+            f = self.filters()
+            self._weights = _lib.make_stack_weights(f["rgc"], f["rgby"], f["stripe"], f["blur"], f["end"])
+            self._weights_key = key
+        return self._weights
+
+    def _device(self):
+        _ops._require_cuda()
+        return self.device if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def _region(self):
+        rh, rw = self.region_shape[1], self.region_shape[2]
+        if int(rh) != rh or int(rw) != rw:
+            raise ValueError("Ambiguous dimension: %s" % ([rh, rw],))
+        return int(rh), int(rw)
+
+    # -- graph on a pyramid (LineEndDisplayer.run) --------------------------------------------------------------------
+    def run(self, pyramid_tensor, want_points=True):
+        """S1-S8 on a pyramid ``[N, h, w, 3]`` (numpy or CUDA tensor). One fused kernel + the emit kernels."""
+        if self.blur_size != 7:
+            return self.run_unfused(pyramid_tensor, want_points)
+        orient, line_end, gray = _ops.stack_fused(pyramid_tensor, self.stack_weights())
+        points = None
+        if want_points:
+            rh, rw = self._region()
+            points = _ops.max_value_indices_region(gray, rh, rw)
+        return LineEndResult(orient, line_end, gray, points)
+
+    def run_unfused(self, pyramid_tensor, want_points=True):
+        """The same graph through the per-operator kernels (any filter structure, any blur size)."""
+        from .filters import rgc_filter, rgby_filter, orientation_filter
+        from .util.selection import pad_inwards, max_value_indices_region
+        from .util.color import get_value_from_color
+        x = _ops.as_device_tensor(pyramid_tensor)
+        orient = orientation_filter(rgby_filter(rgc_filter(x)), self.blur_size)
+        line_end = _ops.conv2d(orient, self.simplex_end_stop, post=_lib.POST_RELU_CLIP, clip_max=255.0)
+        padded = pad_inwards(line_end, [[0, 0], [2, 2], [2, 2], [0, 0]])
+        gray = get_value_from_color(padded)
+        points = max_value_indices_region(padded, self.region_shape, gray) if want_points else None
+        return LineEndResult(orient, padded, gray, points)
+
+    # -- frames resident in HBM ---------------------------------------------------------------------------------------
+    def plan_for(self, frames):
+        return get_plan(frames.shape[1:], frames.dtype, self.output_colors, self.output_size, self.zoom_ratio,
+                        frames.device)
+
+    def run_frames(self, frames, want_points=True, points_capacity=None, out=None):
+        """frames: CUDA ``[B, H, W, 3]`` uint8/float32 -> LineEndResult over ``B * L`` levels (pyramid + S1-S8).
+
+        ``out`` may carry preallocated ``(orient, padded_line_end, points, count)`` tensors to avoid allocation in a
+        steady-state loop; ``points`` then holds ``count`` valid rows (no host sync is performed in that case).
+        """
+        frames = frames if frames.dim() == 4 else frames.unsqueeze(0)
+        frames = frames.contiguous()
+        plan = self.plan_for(frames)
+        b = int(frames.shape[0])
+        plan.reserve(b)
+        n = b * plan.levels
+        dev = frames.device
+        if out is None:
+            orient = torch.empty((n, plan.h, plan.w, 3), dtype=torch.float32, device=dev)
+            line_end = torch.empty_like(orient)
+            cap = int(points_capacity) if points_capacity else max(64 * n, 1024)
+            points = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
+        else:
+            orient, line_end, points, count = out
+            cap = int(points.shape[0])
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().silent_pipeline_run(
+                plan.handle, ctypes.byref(self.stack_weights()), _ops.ptr(frames), b, None, _ops.ptr(orient),
+                _ops.ptr(line_end), _ops.ptr(points), cap, _ops.ptr(count) if want_points else None,
+                _ops.stream_ptr()), "silent_pipeline_run")
+        if out is not None:
+            return LineEndResult(orient, line_end, None, points)
+        if not want_points:
+            return LineEndResult(orient, line_end, None, None)
+        total = int(count.item())
+        if total > cap:   # rare (e.g. an all-black level emits every pixel): redo the emit with room for everything
+            return self.run_frames(frames, want_points, points_capacity=total)
+        return LineEndResult(orient, line_end, None, points[:total])
+
+    # -- host buffers on both sides (LineEndDisplayer.callback) -----------------------------------------------------------
+    def run_host(self, frames, orient_out=None, line_end_out=None, points_capacity=4096):
+        """frames: host numpy ``[B, H, W, 3]`` (ideally page-locked) -> host numpy results via the C-ABI host call."""
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim == 3:
+            frames = frames[np.newaxis]
+        if frames.dtype != np.uint8:
+            frames = frames.astype(np.float32)
+        dev = self._device()
+        tdtype = torch.uint8 if frames.dtype == np.uint8 else torch.float32
+        plan = get_plan(frames.shape[1:], tdtype, self.output_colors, self.output_size, self.zoom_ratio, dev)
+        b = frames.shape[0]
+        n = b * plan.levels
+        if orient_out is None:
+            orient_out = np.empty((n, plan.h, plan.w, 3), np.float32)
+        if line_end_out is None:
+            line_end_out = np.empty((n, plan.h, plan.w, 3), np.float32)
+        points = np.empty((points_capacity, 4), np.int64)
+        count = ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().silent_pipeline_run_host(
+                plan.handle, ctypes.byref(self.stack_weights()), frames.ctypes.data, b, orient_out.ctypes.data,
+                line_end_out.ctypes.data, points.ctypes.data, points_capacity, ctypes.byref(count),
+                _ops.stream_ptr()), "silent_pipeline_run_host")
+        return LineEndResult(orient_out, line_end_out, None, points[:min(count.value, points_capacity)])
+
+    def callback(self, frame, cam_id=None, depth=2):
+        """Per-frame entry point with the reference's signature (``recognition_testing.py:136-144``).
+
+        Returns ``[frame, [orient level images...], [padded_line_end level images...], points]``: the two result
+        tensors on the north-star path as per-level host images, plus the feature points the reference builds but never
+        fetches.
+        """
+        res = self.run_host(np.asarray(frame))
+        return [frame, [res.orient[i] for i in range(res.orient.shape[0])],
+                [res.padded_line_end[i] for i in range(res.padded_line_end.shape[0])], res.points]

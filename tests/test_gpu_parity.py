@@ -1,0 +1,323 @@
+"""GPU parity: every CUDA entry point, called through the C ABI, against the oracle.
+
+Bars (north_star): feature-point indices bit-exact; float32 responses within 1e-5 relative. Because center-surround
+outputs are differences of large sums, "relative" is taken against the tensor's peak magnitude:
+``|a - b| <= 1e-5 * max|ref|``. Against the bit-defined C oracle (same canonical evaluation order) the
+bar is stricter: bitwise equality of every finite value and identical NaN masks.
+"""
+import numpy as np
+import pytest
+
+from conftest import structured_frame, synthetic_frame
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # north_star tolerance
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert built_lib.silent_device_count() >= 1
+
+
+def assert_bits(actual, expected, what):
+    a = actual.detach().cpu().numpy() if isinstance(actual, torch.Tensor) else np.asarray(actual)
+    e = np.asarray(expected)
+    assert a.shape == e.shape, (what, a.shape, e.shape)
+    nan_a, nan_e = np.isnan(a), np.isnan(e)
+    assert np.array_equal(nan_a, nan_e), "%s: NaN masks differ (%d vs %d)" % (what, nan_a.sum(), nan_e.sum())
+    same = (a == e) | nan_e
+    assert same.all(), "%s: %d of %d values differ from the bit-defined oracle, max |d| = %g" % (
+        what, (~same).sum(), same.size, np.nanmax(np.abs(a - e)))
+
+
+def assert_close(actual, expected, what, tol=REL_TOL):
+    a = actual.detach().cpu().numpy() if isinstance(actual, torch.Tensor) else np.asarray(actual)
+    e = np.asarray(expected)
+    assert a.shape == e.shape, (what, a.shape, e.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(e)), "%s: NaN masks differ" % what
+    peak = np.nanmax(np.abs(e)) if np.isfinite(e).any() else 1.0
+    err = np.nanmax(np.abs(a - e)) if np.isfinite(e).any() else 0.0
+    assert err <= tol * max(peak, 1e-30), "%s: max |d| = %g > %g * peak %g" % (what, err, tol, peak)
+
+
+# ---- pyramid -----------------------------------------------------------------------------------------------------------
+
+def test_pyramid_matches_reference_goldens(goldens, c_oracle):
+    from pysilent_b200.util import zoom
+    P = goldens["pyramid"]
+    for name in [k[:-8] for k in P.files if k.endswith("_pyramid")]:
+        img = P[name + "_image"]
+        cw, ch, sc = P[name + "_params"]
+        got = zoom.from_image(img, img.shape[2], [int(cw), int(ch)], float(sc))
+        assert_close(got, P[name + "_pyramid"], "pyramid golden " + name)          # reference's own from_image output
+        assert_bits(got, c_oracle.from_image(img, img.shape[2], [int(cw), int(ch)], float(sc)), "pyramid C " + name)
+        got_f32 = zoom.from_image(img.astype(np.float32), img.shape[2], [int(cw), int(ch)], float(sc))
+        assert_bits(got_f32, got.cpu().numpy(), "pyramid float32 frames " + name)
+
+
+@pytest.mark.parametrize("shape,center,scale", [((480, 640), (288, 192), 1.3), ((480, 640), (288, 192), np.e ** .5),
+                                                ((1080, 1920), (288, 192), 2 ** .5), ((720, 1280), (288, 192), 2 ** .5)])
+def test_pyramid_full_size_bit_exact(shape, center, scale, c_oracle):
+    from pysilent_b200.util import zoom
+    frames = np.stack([synthetic_frame(2, i, *shape) for i in range(2)])
+    got = zoom.from_image(frames, 3, center, scale)
+    want = c_oracle.from_image(frames, 3, center, scale)
+    assert_bits(got, want, "pyramid %s" % (shape,))
+
+
+def test_pyramid_against_literal_oracle_and_properties():
+    from oracle import silent_oracle as lit
+    from pysilent_b200.util import zoom
+    img = synthetic_frame(1, 0, 480, 640)
+    got = zoom.from_image(img, 3, (288, 192), 1.3)
+    assert tuple(got.shape) == (4, 192, 288, 3)
+    assert_close(got, lit.from_image(img, 3, (288, 192), 1.3), "pyramid literal 640x480")
+    # a constant image stays constant on every fully covered level (spline weights sum to 1)
+    flat = np.full((480, 640, 3), 77, np.uint8)
+    out = zoom.from_image(flat, 3, (288, 192), 1.3).cpu().numpy()
+    assert np.abs(out - 77).max() < 1e-3
+    # single channel and 4-channel frames taking 3 colours
+    gray = zoom.from_image(img[:, :, :1], 1, (288, 192), 1.3)
+    assert_bits(gray[..., 0], got[..., 0].cpu().numpy(), "1-channel pyramid")
+    rgba = np.concatenate([img, img[:, :, :1]], axis=2)
+    assert_bits(zoom.from_image(rgba, 3, (288, 192), 1.3), got.cpu().numpy(), "4-channel frame, 3 colours")
+
+
+def test_pyramid_edge_cases():
+    from pysilent_b200.util import zoom
+    small = synthetic_frame(9, 0, 100, 150)
+    out = zoom.from_image(small, 3, (288, 192), 1.5)      # image smaller than the centre: zero levels
+    assert tuple(out.shape) == (0, 192, 288, 3)
+    with pytest.raises(AssertionError):
+        zoom.from_image(small, 3, (288, 192), 1.0)
+    with pytest.raises(AssertionError):
+        zoom.from_image(small, 0, (288, 192), 1.5)
+    with pytest.raises(AssertionError):
+        zoom.from_image(small, 3, (0, 192), 1.5)
+
+
+# ---- per-operator kernels ------------------------------------------------------------------------------------------------
+
+def _pyr(seed, n=3, h=40, w=56, c=3):
+    return (np.random.RandomState(seed).rand(n, h, w, c) * 255).astype(np.float32)
+
+
+def test_filter_callables_bit_exact(c_oracle, default_filters):
+    from oracle import silent_oracle as lit
+    from pysilent_b200 import filters
+    x = _pyr(3)
+    a = filters.rgc_filter(torch.from_numpy(x).cuda())
+    assert_bits(a, c_oracle.conv2d(x, default_filters["rgc"], post=1), "rgc_filter")
+    assert_close(a, lit.conv_relu(x, default_filters["rgc"]), "rgc_filter literal")
+    b = filters.rgby_filter(a)
+    b_ref = c_oracle.conv2d(a.cpu().numpy(), default_filters["rgby"], post=1)
+    assert_bits(b, b_ref, "rgby_filter")
+    assert_close(b, lit.conv_relu(a.cpu().numpy(), default_filters["rgby"]), "rgby_filter literal")
+    d = filters.orientation_filter(b)
+    c_ref = c_oracle.conv2d(b_ref, default_filters["stripe"], post=1)
+    d_ref = c_oracle.regulate_tensor(c_ref, default_filters["blur"], 1.0, .1)
+    assert_bits(d, d_ref, "orientation_filter")
+    lit_c = lit.conv_relu(b_ref, default_filters["stripe"])
+    assert_close(d, lit.regulate_tensor(lit_c, default_filters["blur"], 1.0, .1), "orientation_filter literal")
+    d5 = filters.orientation_filter(b, blur_size=5)
+    import pysilent_b200.constant_convolutions as cc
+    assert_bits(d5, c_oracle.regulate_tensor(c_ref, cc.blur_tensor(2, lengths=5), 1.0, .1), "orientation_filter blur 5")
+    # numpy input is accepted like the reference's get_dimensions allows
+    assert_bits(filters.rgc_filter(x), a.cpu().numpy(), "rgc_filter(numpy)")
+
+
+def test_apply_filter_generic_shapes(c_oracle, goldens):
+    from pysilent_b200.util.apply_filter import apply_filter
+    G = goldens["generators"]
+    x3 = _pyr(4, n=2, h=33, w=47)
+    for key in ("rgb_2d_end", "rgb_2d_edge", "rgb_2d_edge_time_diff", "rgb_2d_end_7x7", "rgby_2", "blur_2_default"):
+        out = apply_filter(torch.from_numpy(x3).cuda(), G[key])
+        assert_bits(out, c_oracle.conv2d(x3, G[key]), "apply_filter " + key)
+    x8 = _pyr(5, n=2, h=21, w=30, c=8)
+    for key in ("end_8", "stripe_8", "blur_8"):
+        assert_bits(apply_filter(x8, G[key]), c_oracle.conv2d(x8, G[key]), "apply_filter " + key)
+    # 3 -> 8 slice used by config C4, 1-pixel and 1-row tensors, NaN propagation through a dense conv
+    w38 = G["stripe_8"][:, :, :3, :]
+    assert_bits(apply_filter(x3, w38), c_oracle.conv2d(x3, w38), "apply_filter 3->8")
+    tiny = _pyr(6, n=1, h=1, w=1)
+    assert_bits(apply_filter(tiny, G["rgb_2d_end"]), c_oracle.conv2d(tiny, G["rgb_2d_end"]), "1x1 image")
+    row = _pyr(7, n=2, h=1, w=70)
+    assert_bits(apply_filter(row, G["rgb_2d_edge"]), c_oracle.conv2d(row, G["rgb_2d_edge"]), "1-row image")
+    xn = x3.copy()
+    xn[0, 5, 7, 1] = np.nan
+    assert_bits(apply_filter(xn, G["rgb_2d_end"]), c_oracle.conv2d(xn, G["rgb_2d_end"]), "NaN input")
+
+
+def test_regulate_pow_paths(c_oracle, default_filters):
+    from pysilent_b200.util.regulator import regulate_tensor
+    rs = np.random.RandomState(8)
+    x = (rs.rand(2, 30, 41, 3) ** 6 * 0.2).astype(np.float32)     # blurred values straddle 1 -> both gain branches
+    x[0, :12, :12] = 0                                             # exact zeros -> 0 * inf = NaN
+    for root in (.1, .5, 1.0):
+        got = regulate_tensor(x, default_filters["blur"], 1.0, root)
+        want = c_oracle.regulate_tensor(x, default_filters["blur"], 1.0, root)
+        assert np.isnan(want).any() and (want != x)[~np.isnan(want)].any()
+        assert_bits(got, want, "regulate root %g" % root)
+    from oracle import silent_oracle as lit
+    assert_close(regulate_tensor(x, default_filters["blur"], 1.0, .1),
+                 lit.regulate_tensor(x, default_filters["blur"], 1.0, .1), "regulate literal", tol=2e-5)
+
+
+def test_pad_value_selection_ops(c_oracle):
+    from oracle import silent_oracle as lit
+    from pysilent_b200.util.selection import pad_inwards, max_value_indices_region, top_value_points
+    from pysilent_b200.util.color import get_value_from_color
+    x = _pyr(9, n=3, h=32, w=48)
+    x[1, 10, 10, 0] = np.nan
+    x[2] = 0                      # all-zero level: every pixel equals its region maximum
+    pads = [[0, 0], [2, 2], [2, 2], [0, 0]]
+    p = pad_inwards(x, pads)
+    assert_bits(p, lit.pad_inwards(x, pads), "pad_inwards")
+    assert_bits(pad_inwards(x, [[0, 0], [1, 3], [0, 5], [0, 0]]), lit.pad_inwards(x, [[0, 0], [1, 3], [0, 5], [0, 0]]),
+                "pad_inwards asymmetric")
+    g = get_value_from_color(p)
+    g_ref = lit.get_value_from_color(lit.pad_inwards(x, pads))
+    assert_bits(g, g_ref, "get_value_from_color")
+    pts = max_value_indices_region(p, [1, 16, 24, 3], g).cpu().numpy()
+    want = lit.max_value_indices_region(lit.pad_inwards(x, pads), [1, 16, 24, 3], g_ref)
+    assert pts.dtype == np.int64 and np.array_equal(pts, want), (pts.shape, want.shape)
+    assert (want[:, 0] == 2).sum() == 32 * 48 and (want[:, 0] == 1).sum() == 0    # zero level emits all, NaN level none
+    c_pts, _ = c_oracle.max_value_indices_region(g_ref, (16, 24))
+    assert np.array_equal(pts, c_pts)
+    # value tensor computed internally, odd region split (3 x 3 overlapping windows)
+    pts2 = max_value_indices_region(p, [1, 11, 16, 3]).cpu().numpy()
+    assert np.array_equal(pts2, lit.max_value_indices_region(lit.pad_inwards(x, pads), [1, 11, 16, 3]))
+    with pytest.raises(ValueError):
+        max_value_indices_region(p, [1, 7.5, 24, 3], g)
+    for pct in (.1, .5, 0.0):
+        t = top_value_points(p, pct, g)
+        assert_bits(t, lit.top_value_points(lit.pad_inwards(x, pads), pct, g_ref), "top_value_points %g" % pct)
+
+
+# ---- fused stack ---------------------------------------------------------------------------------------------------------
+
+def _check_stack(res, ref_c, ref_lit, what):
+    assert_bits(res.orient, ref_c["orient"], what + " orient (C oracle)")
+    assert_bits(res.padded_line_end, ref_c["padded"], what + " padded_line_end (C oracle)")
+    if res.gray is not None:
+        assert_bits(res.gray, ref_c["gray"], what + " gray (C oracle)")
+    pts = res.points.cpu().numpy() if isinstance(res.points, torch.Tensor) else res.points
+    assert np.array_equal(pts, ref_c["points"]), what + " points (C oracle)"
+    if ref_lit is not None:
+        assert_close(res.orient, ref_lit["orient"], what + " orient (literal)", tol=2e-5)
+        assert_close(res.padded_line_end, ref_lit["padded"], what + " padded_line_end (literal)")
+        assert np.array_equal(pts, ref_lit["points"]), what + " points (literal)"
+
+
+def test_fused_stack_matches_reference_goldens(goldens, c_oracle, default_filters):
+    from pysilent_b200 import LineEndPipeline
+    S = goldens["stack"]
+    for name in ("noise", "noise_odd", "natural", "flat"):
+        pyr = S[name + "_pyramid"]
+        pipe = LineEndPipeline(output_size=(pyr.shape[2], pyr.shape[1]))
+        res = pipe.run(pyr)
+        ref_c = c_oracle.line_end_stack(pyr, default_filters)
+        ref_lit = {k: S[name + "_" + k] for k in ("orient", "padded", "points")}     # reference code on the TF-1 shim
+        _check_stack(res, ref_c, ref_lit, "golden " + name)
+        unfused = pipe.run_unfused(pyr)
+        _check_stack(unfused, ref_c, None, "golden unfused " + name)
+
+
+@pytest.mark.parametrize("seed,n,h,w", [(31, 2, 64, 96), (32, 1, 37, 53), (33, 3, 192, 288), (34, 2, 5, 9)])
+def test_fused_stack_bit_exact_random(seed, n, h, w, c_oracle, default_filters):
+    from oracle import silent_oracle as lit
+    from pysilent_b200 import LineEndPipeline
+    pyr = _pyr(seed, n, h, w)
+    pipe = LineEndPipeline(output_size=(w - w % 2, h - h % 2))
+    orient, line_end, gray = __import__("pysilent_b200")._ops.stack_fused(pyr, pipe.stack_weights())
+    ref = c_oracle.line_end_stack(pyr, default_filters)
+    assert_bits(orient, ref["orient"], "orient")
+    assert_bits(line_end, ref["padded"], "padded_line_end")
+    assert_bits(gray, ref["gray"], "gray")
+    ref_lit = lit.line_end_stack(pyr, default_filters)
+    assert_close(orient, ref_lit["orient"], "orient literal")
+    assert_close(line_end, ref_lit["padded"], "padded literal")
+
+
+def test_fused_stack_rejects_unstructured_weights():
+    from pysilent_b200 import LineEndPipeline, _lib, _ops
+    pipe = LineEndPipeline()
+    f = pipe.filters()
+    f["stripe"] = f["stripe"].copy()
+    f["stripe"][0, 0, 1, 0] += 1.0
+    w = _lib.make_stack_weights(f["rgc"], f["rgby"], f["stripe"], f["blur"], f["end"])
+    with pytest.raises(RuntimeError, match="stripe filter differs"):
+        _ops.stack_fused(_pyr(1, 1, 16, 16), w)
+
+
+# ---- whole pipeline ------------------------------------------------------------------------------------------------------
+
+def _oracle_pipeline(c_oracle, frames, center, scale, filters):
+    pyr = c_oracle.from_image(frames, 3, center, scale)
+    return pyr, c_oracle.line_end_stack(pyr, filters)
+
+
+@pytest.mark.parametrize("config,shape,scale,batch", [(1, (480, 640), 1.3, 1), (2, (1080, 1920), 2 ** .5, 1),
+                                                      (5, (720, 1280), 2 ** .5, 3)])
+def test_pipeline_baseline_configs_bit_exact(config, shape, scale, batch, c_oracle, default_filters):
+    """BASELINE configs C1 / C2 / C5 (frame shapes and level counts), device-resident and host-buffer entry points."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(config, i, *shape) for i in range(batch)])
+    pipe = LineEndPipeline(zoom_ratio=scale)
+    pyr, ref = _oracle_pipeline(c_oracle, frames, (288, 192), scale, default_filters)
+    res = pipe.run_frames(torch.from_numpy(frames).cuda())
+    assert tuple(res.orient.shape) == pyr.shape
+    _check_stack(res, ref, None, "config %d device" % config)
+    host = pipe.run_host(frames)
+    _check_stack(host, ref, None, "config %d host" % config)
+    cb = pipe.callback(frames[0])
+    assert cb[0] is frames[0] or np.array_equal(cb[0], frames[0])
+    assert len(cb[1]) == pyr.shape[0] // batch and np.array_equal(cb[1][0], ref["orient"][0], equal_nan=True)
+
+
+def test_pipeline_structured_frames_nan_and_gain_paths(c_oracle, default_filters):
+    from oracle import silent_oracle as lit
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([structured_frame(41 + i, 480, 640) for i in range(2)])
+    pipe = LineEndPipeline(zoom_ratio=1.3)
+    pyr, ref = _oracle_pipeline(c_oracle, frames, (288, 192), 1.3, default_filters)
+    assert np.isnan(ref["orient"]).any(), "the structured frame must exercise the 0 * inf path"
+    res = pipe.run_frames(torch.from_numpy(frames).cuda())
+    ref_lit = lit.line_end_stack(lit.from_image(frames[0], 3, (288, 192), 1.3), default_filters)
+    _check_stack(res, ref, None, "structured")
+    n0 = ref_lit["orient"].shape[0]
+    assert_close(res.orient[:n0], ref_lit["orient"], "structured orient literal", tol=2e-5)
+    lit_pts = ref_lit["points"]
+    got_pts = res.points.cpu().numpy()
+    assert np.array_equal(got_pts[got_pts[:, 0] < n0], lit_pts)
+
+
+def test_pipeline_properties_at_full_size(default_filters):
+    """Size-independent properties on the BASELINE C3 shape (1080p, batch 8): batch independence, determinism,
+    idempotence of the mask, point rows sorted and inside the border."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(3, i, 1080, 1920) for i in range(8)])
+    pipe = LineEndPipeline(zoom_ratio=2 ** .5)
+    dev = torch.from_numpy(frames).cuda()
+    full = pipe.run_frames(dev)
+    again = pipe.run_frames(dev)
+    assert torch.equal(full.orient, again.orient) and torch.equal(full.points, again.points)
+    L = full.orient.shape[0] // 8
+    for i in (0, 5):
+        one = pipe.run_frames(dev[i:i + 1])
+        assert torch.equal(one.orient, full.orient[i * L:(i + 1) * L])
+        assert torch.equal(one.padded_line_end, full.padded_line_end[i * L:(i + 1) * L])
+        sel = full.points[(full.points[:, 0] >= i * L) & (full.points[:, 0] < (i + 1) * L)].clone()
+        sel[:, 0] -= i * L
+        assert torch.equal(one.points, sel)
+    pts = full.points.cpu().numpy()
+    key = (pts[:, 0] * 192 + pts[:, 1]) * 288 + pts[:, 2]
+    assert (np.diff(key) > 0).all() and (pts[:, 3] == 0).all()
+    p = full.padded_line_end
+    assert float(p[:, :2].abs().max()) == 0 and float(p[:, :, -2:].abs().max()) == 0
+    assert float(p.max()) <= 255.0 and float(p.min()) >= 0.0 and float(full.orient.min()) >= 0.0
+    from pysilent_b200.util.selection import pad_inwards
+    assert torch.equal(pad_inwards(p, [[0, 0], [2, 2], [2, 2], [0, 0]]), p)
