@@ -70,6 +70,8 @@ typedef struct silent_stack_weights {
 
 int silent_abi_version(void);
 const char *silent_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (bench.py reports the delta per step). */
+int64_t silent_launch_count(void);
 /* Number of CUDA devices visible, or a negative status. */
 int silent_device_count(void);
 
@@ -152,6 +154,12 @@ int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const sile
 int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
                         float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
                         int64_t capacity, int64_t *count_dev, silent_stream stream);
+
+/* Measurement hook: when enabled, silent_pipeline_run brackets its stages with CUDA events on the launching stream.
+ * silent_plan_stage_ms synchronises those events and returns the device time of the LAST run's pyramid, fused-stack and
+ * emit stages in milliseconds. */
+int silent_plan_enable_timing(silent_plan *plan, int enable);
+int silent_plan_stage_ms(silent_plan *plan, float *pyramid_ms, float *stack_ms, float *emit_ms);
 
 /* Same, with HOST buffers on both sides: the drop-in for LineEndDisplayer.callback (recognition_testing.py:136-144):
  * frames_host [batch,H,W,frame_c] -> orient_host, line_end_host [batch*L,h,w,3], points_host [capacity][4], *count_host.

@@ -13,7 +13,20 @@ from . import silent_oracle as lit
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "silent_oracle.c")
-_OUT = os.path.join(_HERE, "_build", "libsilent_oracle.so")
+
+
+def _has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " fma " in f.read()
+    except OSError:
+        return False
+
+
+# With -mfma, fmaf() compiles to one vfmadd instruction instead of a libm call: same bits, ~20x faster. The flavour is
+# part of the file name so a .so built on an FMA host is never loaded on a CPU without FMA.
+_FMA = _has_fma()
+_OUT = os.path.join(_HERE, "_build", "libsilent_oracle_fma.so" if _FMA else "libsilent_oracle.so")
 _lib = None
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -26,8 +39,8 @@ def build(force=False):
     if not force and os.path.exists(_OUT) and os.path.getmtime(_OUT) >= os.path.getmtime(_SRC):
         return _OUT
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
-    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", _OUT, _SRC,
-                           "-lm"])
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math"] +
+                          (["-mfma"] if _FMA else []) + ["-o", _OUT, _SRC, "-lm"])
     return _OUT
 
 

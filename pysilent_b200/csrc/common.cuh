@@ -12,6 +12,7 @@
 namespace silent {
 
 void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
 int fail(int status, const char *fmt, ...);
 
 #define SILENT_CUDA(call)                                                                                     \
@@ -27,6 +28,7 @@ int fail(int status, const char *fmt, ...);
         cudaError_t err__ = cudaGetLastError();                                                               \
         if (err__ != cudaSuccess)                                                                             \
             return ::silent::fail(SILENT_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(err__)); \
+        ::silent::count_launch();                                                                             \
     } while (0)
 
 constexpr int kTaps = 6;       // order-5 spline: 6 taps per axis

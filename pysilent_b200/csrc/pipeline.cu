@@ -55,6 +55,8 @@ using namespace silent;
 
 silent_plan::~silent_plan()
 {
+    for (cudaEvent_t e : ev)
+        if (e) cudaEventDestroy(e);
     release(ws);
     if (d_tables) cudaFree(d_tables);
 }
@@ -84,9 +86,7 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     SILENT_CUDA(cudaMalloc(&ws.d_select, ws.select_bytes));
     SILENT_CUDA(cudaMalloc(&ws.d_points, ws.points_capacity * 4 * sizeof(int64_t)));
     SILENT_CUDA(cudaMalloc(&ws.d_count, sizeof(int64_t)));
-    SILENT_CUDA(cudaMallocHost(&ws.h_frames, frame_bytes(plan) * max_batch));
-    SILENT_CUDA(cudaMallocHost(&ws.h_orient, tensor_bytes));
-    SILENT_CUDA(cudaMallocHost(&ws.h_line_end, tensor_bytes));
+    // h_frames / h_orient / h_line_end (pinned mirrors for PAGEABLE caller buffers) are allocated on first need
     SILENT_CUDA(cudaMallocHost(&ws.h_points, ws.points_capacity * 4 * sizeof(int64_t)));
     SILENT_CUDA(cudaMallocHost(&ws.h_count, sizeof(int64_t)));
     ws.batch = max_batch;
@@ -110,14 +110,40 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
     cudaStream_t s = (cudaStream_t)stream;
     const int n = batch * plan->levels;
     float *pyr = pyramid_dev ? pyramid_dev : ws.d_pyramid;
+    const bool timing = plan->timing;
+    if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[0], s));
     int rc = pyramid_build(plan, frames_dev, batch, pyr, s);
     if (rc != SILENT_OK) return rc;
+    if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
     rc = stack_fused(pyr, n, plan->h, plan->w, weights_host, orient_dev, line_end_dev, ws.d_gray, s);
     if (rc != SILENT_OK) return rc;
+    if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
     if (count_dev)
         rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
                                       count_dev, ws.d_select, ws.select_bytes, s);
+    if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[3], s));
     return rc;
+}
+
+int silent_plan_enable_timing(silent_plan *plan, int enable)
+{
+    if (!plan) return fail(SILENT_E_INVAL, "null plan");
+    if (enable)
+        for (cudaEvent_t &e : plan->ev)
+            if (!e) SILENT_CUDA(cudaEventCreate(&e));
+    plan->timing = enable != 0;
+    return SILENT_OK;
+}
+
+int silent_plan_stage_ms(silent_plan *plan, float *pyramid_ms, float *stack_ms, float *emit_ms)
+{
+    if (!plan) return fail(SILENT_E_INVAL, "null plan");
+    if (!plan->timing || !plan->ev[3]) return fail(SILENT_E_INVAL, "timing is not enabled on this plan");
+    SILENT_CUDA(cudaEventSynchronize(plan->ev[3]));
+    float *dst[3] = {pyramid_ms, stack_ms, emit_ms};
+    for (int i = 0; i < 3; ++i)
+        if (dst[i]) SILENT_CUDA(cudaEventElapsedTime(dst[i], plan->ev[i], plan->ev[i + 1]));
+    return SILENT_OK;
 }
 
 int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_host,
@@ -136,7 +162,9 @@ int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weig
     const size_t tensor_bytes = n * plan->h * plan->w * 3 * sizeof(float);
 
     const void *src = frames_host;
+    const size_t cap_tensor_bytes = (size_t)ws.batch * plan->levels * plan->h * plan->w * 3 * sizeof(float);
     if (!is_pinned(frames_host)) {
+        if (!ws.h_frames) SILENT_CUDA(cudaMallocHost(&ws.h_frames, frame_bytes(plan) * ws.batch));
         std::memcpy(ws.h_frames, frames_host, in_bytes);
         src = ws.h_frames;
     }
@@ -147,6 +175,9 @@ int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weig
     if (rc != SILENT_OK) return rc;
     const bool orient_direct = orient_host && is_pinned(orient_host);
     const bool line_end_direct = line_end_host && is_pinned(line_end_host);
+    if (orient_host && !orient_direct && !ws.h_orient) SILENT_CUDA(cudaMallocHost(&ws.h_orient, cap_tensor_bytes));
+    if (line_end_host && !line_end_direct && !ws.h_line_end)
+        SILENT_CUDA(cudaMallocHost(&ws.h_line_end, cap_tensor_bytes));
     if (orient_host)
         SILENT_CUDA(cudaMemcpyAsync(orient_direct ? orient_host : ws.h_orient, ws.d_orient, tensor_bytes,
                                     cudaMemcpyDeviceToHost, s));

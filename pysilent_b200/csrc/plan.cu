@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -13,6 +14,9 @@
 namespace silent {
 
 static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -81,6 +85,8 @@ extern "C" {
 int silent_abi_version(void) { return SILENT_ABI_VERSION; }
 
 const char *silent_last_error(void) { return g_error; }
+
+int64_t silent_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int silent_device_count(void)
 {

@@ -46,6 +46,8 @@ struct silent_plan {
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;
     silent::Workspace ws;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before pyramid / stack / emit, after emit
 
     ~silent_plan();
 };

@@ -1,0 +1,121 @@
+"""Pins the two oracles: the literal numpy oracle against outputs of the reference's own code (golden fixtures) and
+against scipy live; the bit-defined C oracle against the literal one to the north-star tolerance."""
+import numpy as np
+import pytest
+
+from conftest import structured_frame, synthetic_frame
+from oracle import silent_oracle as lit
+
+
+def test_pyramid_oracle_equals_reference_from_image(goldens):
+    P = goldens["pyramid"]
+    names = [k[:-8] for k in P.files if k.endswith("_pyramid")]
+    assert len(names) >= 5
+    for name in names:
+        img = P[name + "_image"]
+        cw, ch, sc = P[name + "_params"]
+        got = lit.from_image(img.astype(np.float32), img.shape[2], [int(cw), int(ch)], float(sc))
+        assert np.array_equal(got, P[name + "_pyramid"]), name        # bit-for-bit what scipy produced for the reference
+
+
+def test_zoom_restatement_against_scipy_live():
+    ndimage = pytest.importorskip("scipy.ndimage")
+    rs = np.random.RandomState(5)
+    for (h, w, f) in [(40, 57, 1.0), (61, 90, 1 / 1.3), (200, 311, 1 / 2 ** 1.5), (33, 33, 1 / 5.65), (7, 9, 0.5)]:
+        a = (rs.rand(h, w) * 255).astype(np.float32)
+        want = ndimage.zoom(a, f, order=5, prefilter=False)
+        got = lit.zoom_order5(a, f)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-6 * 255, (h, w, f)
+
+
+def test_level_geometry_matches_survey():
+    # level counts of the BASELINE configs
+    assert lit.pyramid_levels((480, 640), (288, 192), 1.3) == 4
+    assert lit.pyramid_levels((480, 640), (288, 192), np.e ** .5) == 2
+    assert lit.pyramid_levels((1080, 1920), (288, 192), 2 ** .5) == 6
+    assert lit.pyramid_levels((2160, 3840), (288, 192), 2 ** .5) == 8
+    assert lit.pyramid_levels((720, 1280), (288, 192), 2 ** .5) == 5
+    assert lit.level_crop((1080, 1920), (288, 192), 2 ** .5, 5) == [(0, 1080), (145, 1774)]
+
+
+def test_stack_oracle_equals_reference_code_on_shim(goldens, default_filters):
+    S = goldens["stack"]
+    for name in ("noise", "noise_odd", "natural", "flat"):
+        r = lit.line_end_stack(S[name + "_pyramid"], default_filters)
+        for key in ("rgc", "rgby", "orient", "line_end", "padded", "gray"):
+            assert np.array_equal(r[key], S[name + "_" + key], equal_nan=True), (name, key)
+        assert np.array_equal(r["points"], S[name + "_points"]), name
+        top = lit.top_value_points(r["padded"], 0.1, r["gray"])
+        assert np.array_equal(top, S[name + "_top"], equal_nan=True), name
+    assert np.isnan(S["flat_orient"]).any()             # the 0 * inf path is covered
+    assert len(S["flat_points"]) < len(S["noise_points"])
+
+
+def test_c_oracle_against_literal(goldens, default_filters, c_oracle):
+    S = goldens["stack"]
+    for name in ("noise", "noise_odd", "natural", "flat"):
+        pyr = S[name + "_pyramid"]
+        r = c_oracle.line_end_stack(pyr, default_filters)
+        for key in ("rgc", "rgby", "orient", "line_end", "padded", "gray"):
+            a, b = r[key], S[name + "_" + key]
+            assert np.array_equal(np.isnan(a), np.isnan(b)), (name, key)
+            assert np.nanmax(np.abs(a - b)) <= 1e-5 * np.nanmax(np.abs(b)), (name, key)
+        assert np.array_equal(r["points"], S[name + "_points"]), name
+
+
+def test_c_oracle_pyramid_against_goldens(goldens, c_oracle):
+    P = goldens["pyramid"]
+    for name in [k[:-8] for k in P.files if k.endswith("_pyramid")]:
+        img = P[name + "_image"]
+        cw, ch, sc = P[name + "_params"]
+        got = c_oracle.from_image(img, img.shape[2], [int(cw), int(ch)], float(sc))
+        want = P[name + "_pyramid"]
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max(), name
+        assert np.array_equal(got == 0, want == 0) or name == "ragged"    # same undefined-tail rows/cols are zero
+
+
+def test_c_oracle_on_a_real_shape(c_oracle, default_filters):
+    frame = structured_frame(3, 240, 320)
+    pyr_c = c_oracle.from_image(frame, 3, (96, 64), 1.5)
+    pyr_l = lit.from_image(frame, 3, (96, 64), 1.5)
+    assert pyr_c.shape == pyr_l.shape == (4, 64, 96, 3)
+    assert np.abs(pyr_c - pyr_l).max() <= 1e-5 * 255
+    rc, rl = c_oracle.line_end_stack(pyr_l, default_filters), lit.line_end_stack(pyr_l, default_filters)
+    assert np.isnan(rl["orient"]).any()
+    assert np.array_equal(np.isnan(rc["orient"]), np.isnan(rl["orient"]))
+    assert np.nanmax(np.abs(rc["padded"] - rl["padded"])) <= 1e-5 * 255
+    assert np.array_equal(rc["points"], rl["points"])
+
+
+def test_canon_pow(c_oracle):
+    xs = np.float32(np.random.RandomState(0).rand(4000))
+    got = np.array([c_oracle.canon_pow(x, 0.1) for x in xs], np.float32)
+    want = np.power(xs.astype(np.float64), float(np.float32(0.1))).astype(np.float32)
+    assert (got == want).mean() > 0.999 and np.max(np.abs(got - want) / want) < 2e-7
+    assert c_oracle.canon_pow(0, .1) == 0 and c_oracle.canon_pow(1, .1) == 1 and c_oracle.canon_pow(.5, 0) == 1
+    assert np.isnan(c_oracle.canon_pow(-1, .1)) and np.isnan(c_oracle.canon_pow(np.nan, .1))
+    assert c_oracle.canon_pow(1e-45, .1) == pytest.approx(1.4012984643e-45 ** float(np.float32(.1)), rel=1e-6)
+    assert c_oracle.canon_pow(0.25, .5) == 0.5 and c_oracle.canon_pow(0, -1.0) == np.inf
+
+
+def test_emit_edge_cases(c_oracle):
+    g = np.zeros((2, 8, 12, 1), np.float32)
+    g[1, 3, 4, 0] = 5
+    pts = lit.max_value_indices_region(np.repeat(g, 3, -1), [1, 4, 6, 3], g)
+    assert (pts[:, 0] == 0).sum() == 96                     # all-zero level: every pixel qualifies
+    # one bright pixel: it wins every window containing it; quadrants whose window max is 5 emit nothing else
+    assert [tuple(r) for r in pts[pts[:, 0] == 1]] == [(1, 3, 4, 0)]
+    c_pts, count = c_oracle.max_value_indices_region(g, (4, 6))
+    assert count == len(pts) and np.array_equal(c_pts, pts)
+    capped, count2 = c_oracle.max_value_indices_region(g, (4, 6), capacity=10)
+    assert count2 == count and np.array_equal(capped, pts[:10])
+    g[0, 0, 0, 0] = np.nan                                  # NaN poisons every window that contains it
+    pts_nan = lit.max_value_indices_region(np.repeat(g, 3, -1), [1, 4, 6, 3], g)
+    assert np.array_equal(c_oracle.max_value_indices_region(g, (4, 6))[0], pts_nan)
+    assert (pts_nan[:, 0] == 0).sum() < 96
+
+
+def test_synthetic_frames_are_deterministic():
+    a, b = synthetic_frame(2, 7, 48, 64), synthetic_frame(2, 7, 48, 64)
+    assert a.dtype == np.uint8 and np.array_equal(a, b) and not np.array_equal(a, synthetic_frame(2, 8, 48, 64))
