@@ -140,13 +140,16 @@ int silent_top_value_points(const float *color_dev, const float *value_dev, int 
 
 /* ---- fused path ---------------------------------------------------------------------------------------------------- */
 
-/* S1-S7 of LineEndDisplayer.compile (recognition_testing.py:69-77) in one kernel: pyramid_dev [n,h,w,3] ->
+/* S1-S7 of LineEndDisplayer.compile (recognition_testing.py:69-77) fused into two kernels (cut at the one-channel
+ * rgby channel sum, which lives in workspace_dev: silent_stack_workspace_bytes(n, h, w)): pyramid_dev [n,h,w,3] ->
  * orient_dev (orient_tensor), line_end_dev (padded_line_end_tensor), both [n,h,w,3], and gray_dev [n,h,w,1]
  * (gray_line_end_tensor). Any output pointer may be NULL to skip its store. Returns SILENT_E_STRUCTURE when the weights
  * are not (stripe: identical input-channel slices; blur: all slices identical), which the reference's generators
  * always produce. */
+size_t silent_stack_workspace_bytes(int n, int h, int w);
 int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const silent_stack_weights *weights_host,
-                       float *orient_dev, float *line_end_dev, float *gray_dev, silent_stream stream);
+                       float *orient_dev, float *line_end_dev, float *gray_dev, void *workspace_dev,
+                       size_t workspace_bytes, silent_stream stream);
 
 /* The whole hot path for a batch resident in HBM: frames -> pyramid -> S1-S7 -> feature points (S8, region =
  * (h/2, w/2), recognition_testing.py:40,90-91). Uses the plan workspace (silent_plan_reserve(batch) first).

@@ -14,7 +14,7 @@
  *
  * Canonical order, summarised (references are to /root/reference/slam_recognition):
  *  - convolution (util/apply_filter.py:4-7, TF-1 conv2d SAME, cross-correlation): per output channel one fmaf chain
- *    acc = fmaf(W[ky][kx][ci][co], x[y+ky-p][x+kx-p][ci], acc) from +0 in (ky, kx, ci) order, out-of-bounds x = 0.
+ *    acc = fmaf(W[ky][kx][ci][co], x[y+ky-p][x+kx-p][ci], acc) from +0 in (ky, ci, kx) order, out-of-bounds x = 0.
  *    If every input-channel slice of W is bitwise identical ("uniform-in", true for rgb_2d_stripe_tensors and
  *    blur_tensor) the chain runs over the channel sum s = ((x0 + x1) + x2 ...) with W[ky][kx][0][co] in (ky, kx) order.
  *  - relu: acc < 0 ? 0 : acc (NaN propagates).  clip: v > hi ? hi : v.
@@ -22,8 +22,9 @@
  *    gain = value / canon_pow(mm, root) (IEEE float32 divide); out = x * gain.
  *  - canon_pow: exact special cases, else float32(exp2(root * log2(x))) with the double-precision polynomial
  *    log2/exp2 below (only +, *, /, fma on doubles: identical on any IEEE machine, CPU or GPU).
- *  - pyramid (util/zoom/from_image.py:48-64 + scipy zoom order 5): r_j = chain over the 6 x-taps (fmaf, from +0), then
- *    chain over the 6 y-taps of r_j; float32 tap weights supplied by the caller.
+ *  - pyramid (util/zoom/from_image.py:48-64 + scipy zoom order 5): separable, vertical pass first: for each of the 6
+ *    source columns t_i = chain over the 6 y-taps (fmaf, from +0), then the chain over the 6 x-taps of t_i; float32 tap
+ *    weights supplied by the caller.
  */
 #include <math.h>
 #include <stdint.h>
@@ -137,16 +138,19 @@ void so_pyramid(const void *frames, int is_u8, int B, int H, int W, int FC, int 
                         const int *tx = ix + ((size_t)s * w + ox) * 6;
                         const float *gy = wy + ((size_t)s * h + oy) * 6;
                         const float *gx = wx + ((size_t)s * w + ox) * 6;
-                        float acc = 0.0f;
-                        for (int j = 0; j < 6; ++j) {
-                            float r = 0.0f;
-                            for (int i = 0; i < 6; ++i) {
+                        /* vertical pass first: t_i = chain over the 6 y-taps of source column tx[i] ... */
+                        float t[6];
+                        for (int i = 0; i < 6; ++i) {
+                            t[i] = 0.0f;
+                            for (int j = 0; j < 6; ++j) {
                                 size_t off = (((size_t)b * H + ty[j]) * W + tx[i]) * FC + c;
                                 float v = is_u8 ? (float)f8[off] : f32[off];
-                                r = fmaf(gx[i], v, r);
+                                t[i] = fmaf(gy[j], v, t[i]);
                             }
-                            acc = fmaf(gy[j], r, acc);
                         }
+                        /* ... then the chain over the 6 x-taps */
+                        float acc = 0.0f;
+                        for (int i = 0; i < 6; ++i) acc = fmaf(gx[i], t[i], acc);
                         *dst = acc;
                     }
 }
@@ -184,21 +188,23 @@ void so_conv2d(const float *x, int N, int h, int w, int cin, const float *wt, in
             for (int xx = 0; xx < w; ++xx)
                 for (int co = 0; co < cout; ++co) {
                     float acc = 0.0f;
+                    /* chain order: ky outermost, then input channel, then kx (one input row-channel at a time) */
                     for (int ky = 0; ky < kh; ++ky)
-                        for (int kx = 0; kx < kw; ++kx) {
-                            int sy = y + ky - pt, sx = xx + kx - pl;
-                            int inside = sy >= 0 && sy < h && sx >= 0 && sx < w;
-                            const float *px = x + (((size_t)n * h + (inside ? sy : 0)) * w + (inside ? sx : 0)) * cin;
-                            const float *wk = wt + ((size_t)(ky * kw + kx) * cin) * cout + co;
-                            if (uni) {
-                                float s = inside ? px[0] : 0.0f;
-                                for (int ci = 1; ci < cin; ++ci) s = s + (inside ? px[ci] : 0.0f);
-                                acc = fmaf(wk[0], s, acc);
-                            } else {
-                                for (int ci = 0; ci < cin; ++ci)
+                        for (int ci = 0; ci < (uni ? 1 : cin); ++ci)
+                            for (int kx = 0; kx < kw; ++kx) {
+                                int sy = y + ky - pt, sx = xx + kx - pl;
+                                int inside = sy >= 0 && sy < h && sx >= 0 && sx < w;
+                                const float *px =
+                                    x + (((size_t)n * h + (inside ? sy : 0)) * w + (inside ? sx : 0)) * cin;
+                                const float *wk = wt + ((size_t)(ky * kw + kx) * cin) * cout + co;
+                                if (uni) {
+                                    float s = inside ? px[0] : 0.0f;
+                                    for (int c2 = 1; c2 < cin; ++c2) s = s + (inside ? px[c2] : 0.0f);
+                                    acc = fmaf(wk[0], s, acc);
+                                } else {
                                     acc = fmaf(wk[(size_t)ci * cout], inside ? px[ci] : 0.0f, acc);
+                                }
                             }
-                        }
                     if (post >= 1) acc = acc < 0.0f ? 0.0f : acc;
                     if (post >= 2) acc = acc > clip_hi ? clip_hi : acc;
                     out[(((size_t)n * h + y) * w + xx) * cout + co] = acc;

@@ -22,7 +22,7 @@ SYMBOLS = (
     "silent_plan_reserve", "silent_plan_levels", "silent_plan_level_hw", "silent_plan_level_info",
     "silent_plan_level_tables", "silent_plan_algorithmic_bytes", "silent_pyramid_build", "silent_conv2d",
     "silent_regulate", "silent_pad_inwards", "silent_value_from_color", "silent_selection_workspace_bytes",
-    "silent_max_value_indices_region", "silent_top_value_points", "silent_stack_fused", "silent_pipeline_run",
+    "silent_max_value_indices_region", "silent_top_value_points", "silent_stack_workspace_bytes", "silent_stack_fused", "silent_pipeline_run",
     "silent_pipeline_run_host",
 )
 
@@ -77,7 +77,8 @@ def lib():
         "silent_selection_workspace_bytes": (sz, [i, i, i]),
         "silent_max_value_indices_region": (i, [p, i, i, i, i, i, p, i64, p, p, sz, p]),
         "silent_top_value_points": (i, [p, p, i, i, i, i, d, p, p, sz, p]),
-        "silent_stack_fused": (i, [p, i, i, i, ctypes.POINTER(SilentStackWeights), p, p, p, p]),
+        "silent_stack_workspace_bytes": (sz, [i, i, i]),
+        "silent_stack_fused": (i, [p, i, i, i, ctypes.POINTER(SilentStackWeights), p, p, p, p, sz, p]),
         "silent_pipeline_run": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, p, i64, p, p]),
         "silent_pipeline_run_host": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, i64, p, p]),
     }

@@ -159,7 +159,9 @@ def stack_fused(pyramid, weights, want_orient=True, want_line_end=True, want_gra
     orient = mk(3) if want_orient else None
     line_end = mk(3) if want_line_end else None
     gray = mk(1) if want_gray else None
+    nbytes = _lib.lib().silent_stack_workspace_bytes(n, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().silent_stack_fused(ptr(x), n, h, w, ctypes.byref(weights), ptr(orient), ptr(line_end),
-                                                 ptr(gray), stream_ptr()), "silent_stack_fused")
+                                                 ptr(gray), ptr(ws), nbytes, stream_ptr()), "silent_stack_fused")
     return orient, line_end, gray

@@ -55,22 +55,26 @@ __global__ void __launch_bounds__(kConvTileW *kConvTileH)
 #pragma unroll
     for (int co = 0; co < kMaxChannels; ++co) acc[co] = 0.0f;
 
+    // chain order (ky, ci, kx): one input row-channel at a time, as in the register-blocked fused kernels
     for (int ky = 0; ky < k; ++ky) {
-        for (int kx = 0; kx < k; ++kx) {
-            const float *px = s_x + ((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin;
-            const float *pw = s_w + (ky * k + kx) * cin * cout;
-            if (uniform_in) {
+        if (uniform_in) {
+            for (int kx = 0; kx < k; ++kx) {
+                const float *px = s_x + ((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin;
+                const float *pw = s_w + (ky * k + kx) * cin * cout;
                 float s = px[0];
                 for (int ci = 1; ci < cin; ++ci) s = s + px[ci];
 #pragma unroll
                 for (int co = 0; co < kMaxChannels; ++co)
                     if (co < cout) acc[co] = fmaf(pw[co], s, acc[co]);
-            } else {
-                for (int ci = 0; ci < cin; ++ci) {
-                    const float v = px[ci];
+            }
+        } else {
+            for (int ci = 0; ci < cin; ++ci) {
+                for (int kx = 0; kx < k; ++kx) {
+                    const float v = s_x[((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin + ci];
+                    const float *pw = s_w + ((ky * k + kx) * cin + ci) * cout;
 #pragma unroll
                     for (int co = 0; co < kMaxChannels; ++co)
-                        if (co < cout) acc[co] = fmaf(pw[ci * cout + co], v, acc[co]);
+                        if (co < cout) acc[co] = fmaf(pw[co], v, acc[co]);
                 }
             }
         }

@@ -5,6 +5,7 @@
 // -> tf.where. Here: (1) per-window maxima (NaN-propagating), (2) per-row hit counts, (3) exclusive scan over rows,
 // (4) ordered warp-ballot compaction, so the int64 rows (level, y, x, 0) come out in tf.where's row-major order.
 #include "plan.h"
+#include "stack.h"
 
 namespace silent {
 
@@ -184,7 +185,7 @@ __global__ void apply_threshold_kernel(const float *__restrict__ color, const fl
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static size_t selection_bytes(int n, int h, int w)
+size_t selection_bytes(int n, int h, int w)
 {
     const size_t rows = (size_t)n * h;
     (void)w;
@@ -192,9 +193,31 @@ static size_t selection_bytes(int n, int h, int w)
            align_up(rows * sizeof(long long), 256) + 256;
 }
 
+// True when the pooling windows of max_value_indices_region can be reduced inside stack_b_kernel.
+bool window_geometry(int h, int w, int region_h, int region_w, WindowGeom *geo)
+{
+    if (region_h <= 0 || region_w <= 0) return false;
+    const PoolGeom g = pool_geometry(h, w, region_h, region_w);
+    if (g.oh > 2 || g.ow > 2) return false;
+    geo->count = g.oh * g.ow;
+    geo->ow = g.ow;
+    for (int i = 0; i < g.oh; ++i) {
+        const int ya = i * region_h - g.pt;
+        geo->y0[i] = ya > 0 ? ya : 0;
+        geo->y1[i] = ya + h < h ? ya + h : h;
+    }
+    for (int j = 0; j < g.ow; ++j) {
+        const int xa = j * region_w - g.pl;
+        geo->x0[j] = xa > 0 ? xa : 0;
+        geo->x1[j] = xa + w < w ? xa + w : w;
+        if ((geo->x0[j] % 8) != 0 || (geo->x1[j] % 8 != 0 && geo->x1[j] != w)) return false;
+    }
+    return true;
+}
+
 int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
                              int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
-                             cudaStream_t stream)
+                             const int *fused_winmax, cudaStream_t stream)
 {
     if (!value || !count || !workspace || (!points && capacity > 0))
         return fail(SILENT_E_INVAL, "silent_max_value_indices_region: null argument");
@@ -215,8 +238,13 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     ws += align_up((size_t)rows * sizeof(int), 256);
     long long *row_offset = (long long *)ws;
 
-    window_max_kernel<<<dim3(g.oh * g.ow, n), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
-    SILENT_LAUNCH_CHECK("window_max_kernel");
+    if (fused_winmax) {
+        // the stack kernel already reduced the per-region maxima (ordered-int encoding == float bits, NaN = 0x7fc00000)
+        pooled = reinterpret_cast<float *>(const_cast<int *>(fused_winmax));
+    } else {
+        window_max_kernel<<<dim3(g.oh * g.ow, n), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
+        SILENT_LAUNCH_CHECK("window_max_kernel");
+    }
     const int warps_per_block = 8;
     const unsigned blocks = (unsigned)ceil_div(rows, warps_per_block);
     emit_rows_kernel<false><<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_count, nullptr, nullptr, 0);
@@ -248,7 +276,7 @@ int silent_max_value_indices_region(const float *value_dev, int n, int h, int w,
                                     size_t workspace_bytes, silent_stream stream)
 {
     return max_value_indices_region(value_dev, n, h, w, region_h, region_w, points_dev, capacity, count_dev,
-                                    workspace_dev, workspace_bytes, (cudaStream_t)stream);
+                                    workspace_dev, workspace_bytes, nullptr, (cudaStream_t)stream);
 }
 
 int silent_top_value_points(const float *color_dev, const float *value_dev, int n, int h, int w, int c,

@@ -1,17 +1,13 @@
 // The whole hot path behind one call: frames -> pyramid (K1) -> fused stack (K2) -> feature points (K3).
 // silent_pipeline_run works on buffers resident in HBM; silent_pipeline_run_host is the drop-in for
 // LineEndDisplayer.callback (reference recognition_testing.py:136-144) with host buffers on both sides.
+#include <algorithm>
 #include <cstring>
 
 #include "plan.h"
+#include "stack.h"
 
 namespace silent {
-int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
-int stack_fused(const float *pyr, int n, int h, int w, const silent_stack_weights *W, float *orient, float *line_end,
-                float *gray, cudaStream_t stream);
-int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
-                             int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
-                             cudaStream_t stream);
 
 static void release(Workspace &ws)
 {
@@ -21,6 +17,8 @@ static void release(Workspace &ws)
     cudaFree(ws.d_line_end);
     cudaFree(ws.d_gray);
     cudaFree(ws.d_select);
+    cudaFree(ws.d_stack);
+    cudaFree(ws.d_winmax);
     cudaFree(ws.d_points);
     cudaFree(ws.d_count);
     cudaFreeHost(ws.h_frames);
@@ -75,7 +73,8 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     const size_t n = (size_t)max_batch * (plan->levels > 0 ? plan->levels : 1);
     const size_t level_elems = (size_t)plan->h * plan->w;
     const size_t tensor_bytes = n * level_elems * 3 * sizeof(float);
-    const size_t pyr_bytes = n * level_elems * plan->params.num_colors * sizeof(float);
+    size_t pyr_bytes = n * level_elems * plan->params.num_colors * sizeof(float);
+    if (pyramid_pair_supported(plan)) pyr_bytes = std::max(pyr_bytes, pyramid_pair_bytes(plan, max_batch));
     ws.select_bytes = silent_selection_workspace_bytes((int)n, plan->h, plan->w);
     ws.points_capacity = (int64_t)n * 64;
     SILENT_CUDA(cudaMalloc(&ws.d_frames, frame_bytes(plan) * max_batch));
@@ -84,6 +83,9 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     SILENT_CUDA(cudaMalloc(&ws.d_line_end, tensor_bytes));
     SILENT_CUDA(cudaMalloc(&ws.d_gray, n * level_elems * sizeof(float)));
     SILENT_CUDA(cudaMalloc(&ws.d_select, ws.select_bytes));
+    ws.stack_bytes = stack_workspace_bytes((int)n, plan->h, plan->w);
+    SILENT_CUDA(cudaMalloc(&ws.d_stack, ws.stack_bytes));
+    SILENT_CUDA(cudaMalloc(&ws.d_winmax, n * 4 * sizeof(int)));
     SILENT_CUDA(cudaMalloc(&ws.d_points, ws.points_capacity * 4 * sizeof(int64_t)));
     SILENT_CUDA(cudaMalloc(&ws.d_count, sizeof(int64_t)));
     // h_frames / h_orient / h_line_end (pinned mirrors for PAGEABLE caller buffers) are allocated on first need
@@ -109,18 +111,33 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
         return fail(SILENT_E_CAPACITY, "plan workspace holds %d frames, need %d: call silent_plan_reserve", ws.batch, batch);
     cudaStream_t s = (cudaStream_t)stream;
     const int n = batch * plan->levels;
-    float *pyr = pyramid_dev ? pyramid_dev : ws.d_pyramid;
+    // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
+    // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
+    const bool pair_path = pyramid_pair_supported(plan);
     const bool timing = plan->timing;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[0], s));
-    int rc = pyramid_build(plan, frames_dev, batch, pyr, s);
-    if (rc != SILENT_OK) return rc;
+    int rc = SILENT_OK;
+    if (pyramid_dev || !pair_path) {
+        rc = pyramid_build(plan, frames_dev, batch, pyramid_dev ? pyramid_dev : ws.d_pyramid, s);
+        if (rc != SILENT_OK) return rc;
+    }
+    if (pair_path) {
+        rc = pyramid_pair_build(plan, frames_dev, batch, ws.d_pyramid, s);
+        if (rc != SILENT_OK) return rc;
+    }
+    const void *pyr = pair_path ? (const void *)ws.d_pyramid : (const void *)(pyramid_dev ? pyramid_dev : ws.d_pyramid);
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
-    rc = stack_fused(pyr, n, plan->h, plan->w, weights_host, orient_dev, line_end_dev, ws.d_gray, s);
+    WindowGeom geo;
+    const bool fuse_windows = count_dev && window_geometry(plan->h, plan->w, plan->h / 2, plan->w / 2, &geo);
+    if (fuse_windows) SILENT_CUDA(cudaMemsetAsync(ws.d_winmax, 0, (size_t)n * geo.count * sizeof(int), s));
+    rc = stack_fused(pyr, n, plan->h, plan->w, pair_path ? plan->levels : 0, weights_host, orient_dev, line_end_dev,
+                     ws.d_gray, ws.d_stack, ws.stack_bytes, fuse_windows ? &geo : nullptr,
+                     fuse_windows ? ws.d_winmax : nullptr, s);
     if (rc != SILENT_OK) return rc;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
     if (count_dev)
         rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
-                                      count_dev, ws.d_select, ws.select_bytes, s);
+                                      count_dev, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, s);
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[3], s));
     return rc;
 }

@@ -163,6 +163,35 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
         plan->union_w = std::max(plan->union_w, li.x1 - li.x0);
     }
 
+    // geometry of the frame-pair pyramid kernel: per level and x tile, the span of frame-row words its x-taps touch
+    plan->pair.assign(L, PairLevel());
+    plan->pair_ok = L > 0 && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3;
+    for (int s = 0; s < L && plan->pair_ok; ++s) {
+        PairLevel &pl = plan->pair[s];
+        pl.ntx = ceil_div(w, kPairTileW);
+        int widest = 1;
+        for (int t = 0; t < pl.ntx; ++t) {
+            int lo = INT32_MAX, hi = -1;
+            for (int ox = t * kPairTileW; ox < std::min(w, (t + 1) * kPairTileW); ++ox) {
+                const int32_t *tx = &plan->idx_x[((size_t)s * w + ox) * kTaps];
+                if (tx[0] < 0) continue;
+                for (int i = 0; i < kTaps; ++i) lo = std::min(lo, tx[i]), hi = std::max(hi, tx[i]);
+            }
+            if (hi < 0) {
+                pl.word_lo[t] = pl.nwords[t] = 0;
+                continue;
+            }
+            const int byte_lo = lo * p->frame_c, byte_hi = (hi + 1) * p->frame_c;
+            pl.word_lo[t] = byte_lo / 4;
+            pl.nwords[t] = (byte_hi + 3) / 4 - pl.word_lo[t];
+            widest = std::max(widest, pl.nwords[t]);
+        }
+        pl.vpitch = 4 * widest;
+        pl.th = 16;
+        while (pl.th > 1 && (size_t)pl.th * pl.vpitch * 8 > 72 * 1024) pl.th /= 2;
+        if ((size_t)pl.th * pl.vpitch * 8 > 190 * 1024) plan->pair_ok = false;
+    }
+
     if (L > 0) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

@@ -12,16 +12,27 @@ struct LevelInfo {
     int valid_h, valid_w;   // rows / cols the reference actually writes (from_image.py:61-62)
 };
 
+// Launch geometry of pyramid_pair_kernel for one level: x tiles of kPairTileW output columns; per tile the span of
+// aligned 32-bit words of a frame row that its x-taps touch.
+constexpr int kPairTileW = 64, kPairMaxTiles = 64;
+struct PairLevel {
+    int ntx = 0, th = 0, vpitch = 0;
+    int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];
+};
+
 // Plan-owned device scratch, sized by silent_plan_reserve(max_batch).
 struct Workspace {
     int batch = 0;
     void *d_frames = nullptr;      // [B,H,W,FC] staging for *_host calls
-    float *d_pyramid = nullptr;    // [B*L,h,w,C]
+    float *d_pyramid = nullptr;    // [B*L,h,w,C] (NHWC path) or [ceil(B/2)*L][3][h][w] float2 (frame-pair path)
     float *d_orient = nullptr;     // [B*L,h,w,3] staging for *_host calls
     float *d_line_end = nullptr;
     float *d_gray = nullptr;       // [B*L,h,w]
     void *d_select = nullptr;      // selection workspace
     size_t select_bytes = 0;
+    void *d_stack = nullptr;       // fused-stack workspace (paired channel-sum tensor)
+    size_t stack_bytes = 0;
+    int *d_winmax = nullptr;       // [B*L][<=4] per-region maxima reduced inside the stack kernel
     int64_t *d_points = nullptr;   // [points_capacity][4]
     int64_t points_capacity = 0;
     int64_t *d_count = nullptr;
@@ -42,6 +53,8 @@ struct silent_plan {
     std::vector<silent::LevelInfo> info;
     std::vector<int32_t> idx_y, idx_x;   // [L][h|w][6], absolute frame row / column, idx[.][0] = -1 => sample is 0
     std::vector<float> w_y, w_x;
+    std::vector<silent::PairLevel> pair;   // per level
+    bool pair_ok = false;
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;

@@ -1,0 +1,34 @@
+// Internal interface between the fused stack (stack_fused.cu), the emit kernels (emit.cu) and the pipeline.
+#pragma once
+
+#include "common.cuh"
+
+namespace silent {
+
+// Geometry of max_value_indices_region's pooling windows when they can be reduced inside the stack kernel:
+// at most 2 x 2 windows per level and column bounds that are multiples of the 8-pixel run length.
+struct WindowGeom {
+    int count = 0;   // windows per level (0: not fused, the stand-alone window_max kernel is used instead)
+    int ow = 1;      // windows per row of the pooled grid
+    int y0[2] = {0, 0}, y1[2] = {0, 0}, x0[2] = {0, 0}, x1[2] = {0, 0};
+};
+
+size_t stack_workspace_bytes(int n, int h, int w);
+int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
+                float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
+                int *winmax, cudaStream_t stream);
+
+// pyramid.cu
+int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
+bool pyramid_pair_supported(const silent_plan *plan);
+size_t pyramid_pair_bytes(const silent_plan *plan, int batch);
+int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream);
+
+// emit.cu
+bool window_geometry(int h, int w, int region_h, int region_w, WindowGeom *geo);
+int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
+                             int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
+                             const int *fused_winmax, cudaStream_t stream);
+size_t selection_bytes(int n, int h, int w);
+
+}  // namespace silent

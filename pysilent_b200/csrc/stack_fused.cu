@@ -1,272 +1,756 @@
-// K2: the fused stack S1-S7 of LineEndDisplayer.compile (reference recognition_testing.py:69-77) in ONE kernel:
+// K2: the fused stack S1-S7 of LineEndDisplayer.compile (reference recognition_testing.py:69-77):
 //   rgc 3x3 + relu -> rgby 3x3 + relu -> stripe 3x3 + relu -> 7x7 blur regulator -> end 3x3 + relu + clip ->
-//   border mask -> channel mean.
-// Each CTA owns one TH x TW tile of one pyramid level; the input tile (+7 halo) is read from HBM once, every
-// intermediate lives in shared memory, and only orient / line_end / gray are written back. All filter weights arrive as
-// a kernel parameter (constant bank), so there is no global state and no weight traffic.
+//   border mask -> channel mean (+ per-region maxima for the feature-point emit).
 //
-// Structure used (validated on the host, else SILENT_E_STRUCTURE): the stripe filter is identical over its input
-// channels (3x3x3x3 -> three 3x3 kernels on the channel sum) and the blur filter is one 7x7 kernel in every slice
-// (441 MAC -> 49). Both hold for every filter the reference's generators produce. Evaluation order = canonical order of
-// oracle/silent_oracle.c, so results are bit-identical to it.
+// B200 design (measured: v1, one thread per pixel reading shared memory per tap, was instruction-issue bound at ~1400
+// thread-instructions per pixel against ~240 useful FMAs):
+//  * TWO IMAGES IN LOCKSTEP. Every value in shared memory and registers is a float2 (image A, image B) of the same
+//    pixel/channel of two pyramid levels, so every tap is an aligned pair: all arithmetic is FFMA2/FADD2/FMUL2
+//    (sm_100 packed fp32: one issue slot for two FMAs), every shared-memory access is a 128-bit LDS/STS of two pixels,
+//    and the weights ride in uniform registers as (w, w) pairs straight from the kernel-parameter constant bank.
+//  * REGISTER BLOCKING. A thread owns a run of 8 pixels of one row; for each (ky, ci) it loads the 10 (14 for the blur)
+//    input columns once with 128-bit loads and feeds all kx taps / outputs from registers: ~13 FMAs per load.
+//    Lanes of a warp walk ROWS and the row pitch is an odd multiple of 16 B, so the 128-bit accesses are conflict-free.
+//  * TWO KERNELS, CUT AT THE ONE-CHANNEL TENSOR. stack_a: x -> rgc -> rgby -> channel sum b (1 channel, written as
+//    interleaved pairs); stack_b: b -> stripe -> regulator -> end -> outputs. The stripe filter only needs the channel
+//    sum of b, so the cut costs 2 x 1/6 of the output traffic but shrinks halos (2 and 5 instead of 7), which keeps
+//    the redundant halo arithmetic at ~10 % with 32 x 64 tiles.
+//  * zero weights cost nothing: rgc is depthwise and rgby has 28 structural zeros; both patterns are verified on the
+//    host and compiled out (dense variants exist for arbitrary weights).
+// Evaluation order = canonical order of oracle/silent_oracle.c (chains in (ky, ci, kx) order), so results are
+// bit-identical to it. HBM-bound by design; tensor cores do not apply (3-channel fp32 stencils).
 #include <cstring>
+#include <initializer_list>
 
 #include "plan.h"
+#include "stack.h"
 
 namespace silent {
 
-struct StackParams {
-    float w1[9][3][3];   // rgc    [tap][ci][co]
-    float w2[9][3][3];   // rgby
-    float w3[9][3];      // stripe [tap][co]   (uniform over ci)
-    float wb[49];        // blur   [tap]       (uniform over ci, co)
-    float w5[9][3][3];   // end
-    float reg_value, reg_root, clip_max;
-    int border;
-    int h, w;
-};
+typedef float2 f2;
 
-constexpr int kStackThreads = 256;
+__device__ __forceinline__ f2 fma2(f2 w, f2 v, f2 a) { return __ffma2_rn(w, v, a); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 zero2() { return make_float2(0.0f, 0.0f); }
 
-template <int TH, int TW>
-struct StackTile {
-    static constexpr int XH = TH + 14, XW = TW + 14;   // input            (halo 7)
-    static constexpr int AH = TH + 12, AW = TW + 12;   // rgc              (halo 6)
-    static constexpr int BH = TH + 10, BW = TW + 10;   // rgby channel sum (halo 5)
-    static constexpr int CH = TH + 8, CW = TW + 8;     // stripe           (halo 4)
-    static constexpr int DH = TH + 2, DW = TW + 2;     // orient           (halo 1)
-    static constexpr int kBufX = XH * XW * 3;          // X, later C
-    static constexpr int kBufA = AH * AW * 3;          // A, later Csum + D
-    static constexpr int kBufB = BH * BW;              // Bsum
-    static constexpr size_t kSmemBytes = (size_t)(kBufX + kBufA + kBufB) * sizeof(float);
-    static_assert(CH * CW * 3 <= kBufX, "stripe tile must fit in the input buffer");
-    static_assert(CH * CW + DH * DW * 3 <= kBufA, "channel sum + orient tile must fit in the rgc buffer");
-};
-
-template <int TH, int TW>
-__global__ void __launch_bounds__(kStackThreads, 2)
-    stack_fused_kernel(const float *__restrict__ pyr, const __grid_constant__ StackParams P, float *__restrict__ orient,
-                       float *__restrict__ line_end, float *__restrict__ gray)
+// relu / clip that propagate NaN (canon_relu / canon_clip_hi on every reachable value; -0 never occurs)
+__device__ __forceinline__ float relu_nan(float v)
 {
-    using T = StackTile<TH, TW>;
-    extern __shared__ float smem[];
-    float *sX = smem;                 // [XH][XW][3]
-    float *sA = smem + T::kBufX;      // [AH][AW][3]
-    float *sB = sA + T::kBufA;        // [BH][BW]
-    float *sC = sX;                   // [CH][CW][3]   (X is dead once A exists)
-    float *sCs = sA;                  // [CH][CW]      (A is dead once Bsum exists)
-    float *sD = sA + T::CH * T::CW;   // [DH][DW][3]
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float clip_nan(float v, float hi)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 relu2_finite(f2 v) { return make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)); }
+__device__ __noinline__ float slow_gain(float m, float value, float root) { return canon_gain(m, value, root); }
 
-    const int tid = threadIdx.x;
-    const int n = blockIdx.z;
-    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
-    const int h = P.h, w = P.w;
-    const float *img = pyr + (size_t)n * h * w * 3;
+constexpr int kPX = 8;   // pixels per thread run
 
-    // ---- load input tile, zero outside the level (SAME padding of S1) -------------------------------------------------
-    for (int i = tid; i < T::XH * T::XW * 3; i += kStackThreads) {
-        const int r = i / (T::XW * 3), e = i - r * (T::XW * 3);
-        const int gy = ty0 - 7 + r, gx = tx0 - 7 + e / 3;
-        float v = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(img + ((size_t)gy * w + gx) * 3 + (e % 3));
-        sX[i] = v;
-    }
-    __syncthreads();
+// smallest pitch (in float2) >= n whose byte stride is an odd multiple of 16: conflict-free 128-bit row-strided access
+constexpr int round_pitch(int n) { return n + ((2 - n % 4) + 4) % 4; }
 
-    // ---- S1: a = relu(conv3x3(x, rgc))                                                          filters/rgc.py:13-16
-    for (int i = tid; i < T::AH * T::AW; i += kStackThreads) {
-        const int r = i / T::AW, c = i - r * T::AW;
-        const int gy = ty0 - 6 + r, gx = tx0 - 6 + c;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+template <int NQ>
+__device__ __forceinline__ void load_cols(const f2 *__restrict__ src, f2 (&v)[2 * NQ])
+{
+    const float4 *p = reinterpret_cast<const float4 *>(src);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float *px = sX + ((r + t / 3) * T::XW + c + t % 3) * 3;
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const float v = px[ci];
-                    a0 = fmaf(P.w1[t][ci][0], v, a0);
-                    a1 = fmaf(P.w1[t][ci][1], v, a1);
-                    a2 = fmaf(P.w1[t][ci][2], v, a2);
-                }
-            }
-            a0 = canon_relu(a0), a1 = canon_relu(a1), a2 = canon_relu(a2);
-        }
-        sA[i * 3 + 0] = a0, sA[i * 3 + 1] = a1, sA[i * 3 + 2] = a2;
-    }
-    __syncthreads();
-
-    // ---- S2: b = relu(conv3x3(a, rgby)); only the channel sum is needed downstream              filters/rgby.py:11-12
-    for (int i = tid; i < T::BH * T::BW; i += kStackThreads) {
-        const int r = i / T::BW, c = i - r * T::BW;
-        const int gy = ty0 - 5 + r, gx = tx0 - 5 + c;
-        float s = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-            float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float *pa = sA + ((r + t / 3) * T::AW + c + t % 3) * 3;
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const float v = pa[ci];
-                    b0 = fmaf(P.w2[t][ci][0], v, b0);
-                    b1 = fmaf(P.w2[t][ci][1], v, b1);
-                    b2 = fmaf(P.w2[t][ci][2], v, b2);
-                }
-            }
-            s = (canon_relu(b0) + canon_relu(b1)) + canon_relu(b2);
-        }
-        sB[i] = s;
-    }
-    __syncthreads();
-
-    // ---- S3: c = relu(conv3x3(b, stripe)) on the channel sum                              filters/orientation.py:24-29
-    for (int i = tid; i < T::CH * T::CW; i += kStackThreads) {
-        const int r = i / T::CW, c = i - r * T::CW;
-        const int gy = ty0 - 4 + r, gx = tx0 - 4 + c;
-        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float v = sB[(r + t / 3) * T::BW + c + t % 3];
-                c0 = fmaf(P.w3[t][0], v, c0);
-                c1 = fmaf(P.w3[t][1], v, c1);
-                c2 = fmaf(P.w3[t][2], v, c2);
-            }
-            c0 = canon_relu(c0), c1 = canon_relu(c1), c2 = canon_relu(c2);
-        }
-        sC[i * 3 + 0] = c0, sC[i * 3 + 1] = c1, sC[i * 3 + 2] = c2;
-        sCs[i] = (c0 + c1) + c2;
-    }
-    __syncthreads();
-
-    // ---- S4: d = c * (value / pow(min(blur7x7(c), 1), root))                 regulator/gaussian_regulator_tensor.py:34-36
-    for (int i = tid; i < T::DH * T::DW; i += kStackThreads) {
-        const int r = i / T::DW, c = i - r * T::DW;
-        const int gy = ty0 - 1 + r, gx = tx0 - 1 + c;
-        float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-        if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
-            float m = 0.0f;
-#pragma unroll
-            for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 7; ++kx) m = fmaf(P.wb[ky * 7 + kx], sCs[(r + ky) * T::CW + c + kx], m);
-            const float gain = canon_gain(m, P.reg_value, P.reg_root);
-            const float *pc = sC + ((r + 3) * T::CW + c + 3) * 3;
-            d0 = pc[0] * gain, d1 = pc[1] * gain, d2 = pc[2] * gain;
-        }
-        sD[i * 3 + 0] = d0, sD[i * 3 + 1] = d1, sD[i * 3 + 2] = d2;
-    }
-    __syncthreads();
-
-    // ---- orient output (coalesced rows of the central TH x TW)
-    if (orient) {
-        float *dst = orient + (size_t)n * h * w * 3;
-        for (int i = tid; i < TH * TW * 3; i += kStackThreads) {
-            const int r = i / (TW * 3), e = i - r * (TW * 3);
-            const int gy = ty0 + r, gx = tx0 + e / 3;
-            if (gy < h && gx < w) dst[((size_t)gy * w + gx) * 3 + e % 3] = sD[((r + 1) * T::DW + 1) * 3 + e];
-        }
-    }
-
-    // ---- S5-S7: e = clip(relu(conv3x3(d, end))); p = mask * e; g = mean(p)                recognition_testing.py:73-77
-    for (int i = tid; i < TH * TW; i += kStackThreads) {
-        const int r = i / TW, c = i - r * TW;
-        const int gy = ty0 + r, gx = tx0 + c;
-        if (gy >= h || gx >= w) continue;
-        float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float *pd = sD + ((r + t / 3) * T::DW + c + t % 3) * 3;
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                const float v = pd[ci];
-                e0 = fmaf(P.w5[t][ci][0], v, e0);
-                e1 = fmaf(P.w5[t][ci][1], v, e1);
-                e2 = fmaf(P.w5[t][ci][2], v, e2);
-            }
-        }
-        e0 = canon_clip_hi(canon_relu(e0), P.clip_max);
-        e1 = canon_clip_hi(canon_relu(e1), P.clip_max);
-        e2 = canon_clip_hi(canon_relu(e2), P.clip_max);
-        const bool inside = gy >= P.border && gy < h - P.border && gx >= P.border && gx < w - P.border;
-        if (!inside) {
-            e0 = e0 != e0 ? e0 : 0.0f * e0;
-            e1 = e1 != e1 ? e1 : 0.0f * e1;
-            e2 = e2 != e2 ? e2 : 0.0f * e2;
-        }
-        const size_t pix = ((size_t)n * h + gy) * w + gx;
-        if (line_end) {
-            line_end[pix * 3 + 0] = e0;
-            line_end[pix * 3 + 1] = e1;
-            line_end[pix * 3 + 2] = e2;
-        }
-        if (gray) gray[pix] = ((e0 + e1) + e2) * __fdiv_rn(1.0f, 3.0f);
+    for (int q = 0; q < NQ; ++q) {
+        const float4 t = p[q];
+        v[2 * q] = make_float2(t.x, t.y);
+        v[2 * q + 1] = make_float2(t.z, t.w);
     }
 }
 
-static bool bits_equal(float a, float b) { return std::memcmp(&a, &b, 4) == 0; }
+__device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[kPX])
+{
+    float4 *p = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+    for (int q = 0; q < kPX / 2; ++q) p[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+}
 
-// Validate the structure the fused kernel relies on and repack the HWIO filters.
-int pack_stack_params(const silent_stack_weights *W, int h, int w, StackParams *P)
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel A: x (pyramid, NHWC) -> rgc -> rgby -> channel sum, written as pairs bsum2[pair][y][x] = (imgA, imgB)
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct ParamsA {
+    f2 w1[9][3][3];   // rgc  [tap][ci][co] as (w, w)
+    f2 w2[9][3][3];   // rgby
+    int h, w, n;      // level shape, number of images
+    int pair_levels;  // image pairing: pair p holds images (a, a + pair_levels), see pair_images()
+};
+
+// Which two images ride in the float2 lanes of pair p. With pair_levels = 1 these are images (2p, 2p + 1); the
+// pipeline pairs the SAME level of two consecutive frames (pair_levels = levels per frame), which lets the pyramid
+// kernel share its tap tables between the lanes. Lane B mirrors lane A (and is never stored) when it has no image.
+__device__ __forceinline__ void pair_images(int p, int levels, int n, int &a, int &b, bool &has_b)
+{
+    const int frame_pair = p / levels, s = p - frame_pair * levels;
+    a = frame_pair * 2 * levels + s;
+    b = a + levels;
+    has_b = b < n;
+    if (!has_b) b = a;
+}
+
+template <int TH, int TW>
+struct TileA {
+    static constexpr int X_ROWS = TH + 4, A_ROWS = TH + 2;      // x: halo 2 (origin -2), a: halo 1 (origin -1)
+    static constexpr int A_RUNS = (TW + 2 + kPX - 1) / kPX;     // S1 runs start at column -1
+    static constexpr int B_RUNS = TW / kPX;
+    static constexpr int X_PITCH = round_pitch(kPX * (A_RUNS - 1) + 10 > TW + 4 ? kPX * (A_RUNS - 1) + 10 : TW + 4);
+    static constexpr int A_PITCH = round_pitch(kPX * A_RUNS > kPX * (B_RUNS - 1) + 10 ? kPX * A_RUNS : kPX * (B_RUNS - 1) + 10);
+    static constexpr int X_PLANE = X_ROWS * X_PITCH, A_PLANE = A_ROWS * A_PITCH;
+    static constexpr size_t kSmemBytes = (size_t)(3 * X_PLANE + 3 * A_PLANE) * sizeof(f2);
+    static_assert(TW % kPX == 0 && TW % 4 == 0, "tile width must be a multiple of the run length");
+};
+
+// rgby_3 structure: off-centre taps couple only DIFFERENT channels; the centre tap couples each
+// channel with itself and channels 1 <-> 2. Anything else is structurally zero (28 of 81 weights).
+__host__ __device__ constexpr bool rgby_nonzero(int tap, int ci, int co)
+{
+    return tap == 4 ? (ci == co || (ci == 1 && co == 2) || (ci == 2 && co == 1)) : (ci != co);
+}
+
+// PAIRED_IN: the input is xpair[pair][c][y][x] float2 written by pyramid_pair_kernel (a verbatim 128-bit copy into the
+// planes); otherwise it is an NHWC float32 pyramid [n][h][w][3] (stand-alone silent_stack_fused).
+template <int TH, int TW, int NT, bool S1_DEPTHWISE, bool S2_RGBY, bool PAIRED_IN>
+__global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ input, const __grid_constant__ ParamsA P,
+                                                     f2 *__restrict__ bsum2)
+{
+    using T = TileA<TH, TW>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    f2 *sX = reinterpret_cast<f2 *>(smem_raw);   // [3][X_ROWS][X_PITCH]
+    f2 *sA = sX + 3 * T::X_PLANE;                // [3][A_ROWS][A_PITCH]
+
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int h = P.h, w = P.w;
+    int img0, img1;
+    bool has_b;
+    pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
+
+    if (PAIRED_IN) {
+        // ---- load x: the planes are already pair-interleaved: 128-bit = 2 pixels x 2 frames, zero outside the level ----
+        constexpr int QUADS = T::X_PITCH / 2;
+        const f2 *src = reinterpret_cast<const f2 *>(input) + (size_t)pair * 3 * h * w;
+        const bool vec_ok = (w % 2) == 0;
+        for (int i = tid; i < 3 * T::X_ROWS * QUADS; i += NT) {
+            const int q = i % QUADS, rest = i / QUADS;
+            const int r = rest % T::X_ROWS, c = rest / T::X_ROWS;
+            const int gy = ty0 - 2 + r, x0 = tx0 - 2 + 2 * q, x1 = x0 + 1;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (gy >= 0 && gy < h) {
+                const f2 *row = src + ((size_t)c * h + gy) * w;
+                if (vec_ok && x0 >= 0 && x1 < w) {
+                    v = __ldg(reinterpret_cast<const float4 *>(row + x0));
+                } else {
+                    if (x0 >= 0 && x0 < w) {
+                        const f2 a = __ldg(row + x0);
+                        v.x = a.x, v.y = a.y;
+                    }
+                    if (x1 >= 0 && x1 < w) {
+                        const f2 b = __ldg(row + x1);
+                        v.z = b.x, v.w = b.y;
+                    }
+                }
+            }
+            reinterpret_cast<float4 *>(sX + c * T::X_PLANE + r * T::X_PITCH)[q] = v;
+        }
+    } else {
+        // ---- load x: 4-pixel groups (3 x 128-bit) of each image row, scattered into the pair-interleaved planes -------
+        const float *pyr = reinterpret_cast<const float *>(input);
+        constexpr int GROUPS = (TW + 8) / 4;   // columns tx0-4 .. tx0+TW+4
+        float *sXf = reinterpret_cast<float *>(sX);
+        const bool vec_ok = (w % 4) == 0;
+        for (int i = tid; i < 2 * T::X_ROWS * GROUPS; i += NT) {
+            const int g = i % GROUPS, rest = i / GROUPS;
+            const int r = rest % T::X_ROWS, lane = rest / T::X_ROWS;
+            const int gy = ty0 - 2 + r, gx = tx0 - 4 + 4 * g;
+            float vals[12];
+            const bool row_ok = gy >= 0 && gy < h;
+            const float *src = pyr + (((size_t)(lane ? img1 : img0) * h + (row_ok ? gy : 0)) * w) * 3;
+            if (row_ok && vec_ok && gx >= 0 && gx + 4 <= w) {
+                const float4 *p4 = reinterpret_cast<const float4 *>(src + (size_t)gx * 3);
+                const float4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2);
+                vals[0] = a.x, vals[1] = a.y, vals[2] = a.z, vals[3] = a.w, vals[4] = b.x, vals[5] = b.y;
+                vals[6] = b.z, vals[7] = b.w, vals[8] = c.x, vals[9] = c.y, vals[10] = c.z, vals[11] = c.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 12; ++e) {
+                    const int x = gx + e / 3;
+                    vals[e] = (row_ok && x >= 0 && x < w) ? __ldg(src + (size_t)x * 3 + e % 3) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int idx = 4 * g - 2 + p;   // column index in the x planes (origin -2)
+                if (idx >= 0 && idx < T::X_PITCH) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sXf[2 * (c * T::X_PLANE + r * T::X_PITCH + idx) + lane] = vals[3 * p + c];
+                }
+            }
+        }
+        // columns the loader never touches but the last S1 run over-reads
+        constexpr int LOADED = 4 * GROUPS - 2;
+        if (LOADED < T::X_PITCH) {
+            for (int i = tid; i < 3 * T::X_ROWS * (T::X_PITCH - LOADED); i += NT) {
+                const int c = i % (T::X_PITCH - LOADED), rest = i / (T::X_PITCH - LOADED);
+                sX[rest * T::X_PITCH + LOADED + c] = zero2();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- S1: a = relu(conv3x3(x, rgc))   rows -1..TH, runs of 8 columns from -1               filters/rgc.py:13-16
+    for (int t = tid; t < T::A_ROWS * T::A_RUNS; t += NT) {
+        const int r = t % T::A_ROWS, k = t / T::A_ROWS;
+        const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kPX * k;
+        f2 acc[kPX][3];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+        if (gy >= 0 && gy < h) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    f2 v[10];
+                    load_cols<5>(sX + ci * T::X_PLANE + (r + ky) * T::X_PITCH + kPX * k, v);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                            for (int co = 0; co < 3; ++co)
+                                if (!S1_DEPTHWISE || ci == co)
+                                    acc[p][co] = fma2(P.w1[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            f2 out[kPX];
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                const int gx = gx0 + p;
+                out[p] = (gx >= 0 && gx < w) ? relu2_finite(acc[p][co]) : zero2();   // SAME padding of the next conv
+            }
+            store_cols8(sA + co * T::A_PLANE + r * T::A_PITCH + kPX * k, out);
+        }
+    }
+    __syncthreads();
+
+    // ---- S2: b = relu(conv3x3(a, rgby)); only (b0 + b1) + b2 is needed downstream              filters/rgby.py:11-12
+    for (int t = tid; t < TH * T::B_RUNS; t += NT) {
+        const int r = t % TH, k = t / TH;
+        const int gy = ty0 + r, gx0 = tx0 + kPX * k;
+        if (gy >= h || gx0 >= w) continue;
+        f2 acc[kPX][3];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                f2 v[10];
+                load_cols<5>(sA + ci * T::A_PLANE + (r + ky) * T::A_PITCH + kPX * k, v);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                        for (int co = 0; co < 3; ++co)
+                            if (!S2_RGBY || rgby_nonzero(ky * 3 + kx, ci, co))
+                                acc[p][co] = fma2(P.w2[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+            }
+        }
+        f2 s[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p)
+            s[p] = add2(add2(relu2_finite(acc[p][0]), relu2_finite(acc[p][1])), relu2_finite(acc[p][2]));
+        f2 *dst = bsum2 + ((size_t)pair * h + gy) * w + gx0;
+        if (gx0 + kPX <= w && (w % 2) == 0) {
+            store_cols8(dst, s);
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p)
+                if (gx0 + p < w) dst[p] = s[p];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel B: bsum2 -> stripe -> regulator -> end filter -> orient, padded_line_end, gray, per-region maxima
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct ParamsB {
+    f2 w3[9][3];      // stripe [tap][co]  (identical over ci)
+    f2 wb[49];        // blur   [tap]      (identical over ci, co)
+    f2 w5[9][3][3];   // end    [tap][ci][co]
+    float reg_value, reg_root, clip_max;
+    int border;
+    int h, w, n;
+    int pair_levels;  // see pair_images()
+    WindowGeom win;   // fused region maxima (stack.h)
+};
+
+template <int TH, int TW>
+struct TileB {
+    static constexpr int C_RUNS = (TW + 8) / kPX;                 // S3 runs start at column -4 (TW % 8 == 0)
+    static constexpr int D_RUNS = (TW + 2 + kPX - 1) / kPX;       // S4 runs start at column -1
+    static constexpr int E_RUNS = TW / kPX;
+    static constexpr int B_ROWS = TH + 10, CS_ROWS = TH + 8, CD_ROWS = TH + 2;
+    static constexpr int B_PITCH = round_pitch(kPX * (C_RUNS - 1) + 10);                     // origin -5
+    static constexpr int CS_PITCH = round_pitch(kPX * (D_RUNS - 1) + 14 > kPX * C_RUNS ? kPX * (D_RUNS - 1) + 14
+                                                                                       : kPX * C_RUNS);   // origin -4
+    static constexpr int CD_PITCH = round_pitch(kPX * D_RUNS > kPX * (E_RUNS - 1) + 10 ? kPX * D_RUNS
+                                                                                       : kPX * (E_RUNS - 1) + 10);  // -1
+    static constexpr int B_PLANE = B_ROWS * B_PITCH, CS_PLANE = CS_ROWS * CS_PITCH, CD_PLANE = CD_ROWS * CD_PITCH;
+    static constexpr size_t kSmemBytes = (size_t)(B_PLANE + CS_PLANE + 3 * CD_PLANE) * sizeof(f2) + 64;
+    static_assert(TW % kPX == 0, "tile width must be a multiple of the run length");
+};
+
+template <int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
+                                                     float *__restrict__ orient, float *__restrict__ line_end,
+                                                     float *__restrict__ gray, int *__restrict__ winmax)
+{
+    using T = TileB<TH, TW>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
+    f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
+    f2 *sCD = sCs + T::CS_PLANE;                 // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
+    int *sWin = reinterpret_cast<int *>(sCD + 3 * T::CD_PLANE);   // [2 images][4 windows]
+
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int h = P.h, w = P.w;
+    int img0, img1;
+    bool has_b;
+    pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
+
+    if (tid < 8) sWin[tid] = 0;
+
+    // ---- load the channel-sum tile (pairs are already interleaved): 128-bit = 2 pixels x 2 images --------------------
+    {
+        constexpr int QUADS = T::B_PITCH / 2;
+        const f2 *src = bsum2 + (size_t)pair * h * w;
+        const bool vec_ok = (w % 2) == 0;
+        for (int i = tid; i < T::B_ROWS * QUADS; i += NT) {
+            const int q = i % QUADS, r = i / QUADS;
+            const int gy = ty0 - 5 + r;
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const int x0 = tx0 - 5 + 2 * q, x1 = x0 + 1;   // plane column 2q <-> level column tx0 - 5 + 2q
+            if (gy >= 0 && gy < h) {
+                const f2 *row = src + (size_t)gy * w;
+                if (vec_ok && (x0 & 1) == 0 && x0 >= 0 && x1 < w) {
+                    v = __ldg(reinterpret_cast<const float4 *>(row + x0));
+                } else {
+                    if (x0 >= 0 && x0 < w) {
+                        const f2 a = __ldg(row + x0);
+                        v.x = a.x, v.y = a.y;
+                    }
+                    if (x1 >= 0 && x1 < w) {
+                        const f2 b = __ldg(row + x1);
+                        v.z = b.x, v.w = b.y;
+                    }
+                }
+            }
+            reinterpret_cast<float4 *>(sB + r * T::B_PITCH)[q] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- S3: c = relu(conv3x3(b, stripe)) on the channel sum; rows -4..TH+3, runs from column -4   orientation.py:24-29
+    for (int t = tid; t < T::CS_ROWS * T::C_RUNS; t += NT) {
+        const int r = t % T::CS_ROWS, k = t / T::CS_ROWS;
+        const int gy = ty0 - 4 + r, gx0 = tx0 - 4 + kPX * k;
+        f2 acc[kPX][3];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+        if (gy >= 0 && gy < h) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                f2 v[10];
+                load_cols<5>(sB + (r + ky) * T::B_PITCH + kPX * k, v);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                        for (int co = 0; co < 3; ++co) acc[p][co] = fma2(P.w3[ky * 3 + kx][co], v[p + kx], acc[p][co]);
+            }
+        }
+        f2 cs[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) {
+            const int gx = gx0 + p;
+            const bool inside = gx >= 0 && gx < w;
+#pragma unroll
+            for (int co = 0; co < 3; ++co) acc[p][co] = inside ? relu2_finite(acc[p][co]) : zero2();
+            cs[p] = add2(add2(acc[p][0], acc[p][1]), acc[p][2]);
+        }
+        store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
+        const int rd = r - 3;   // row in the CD planes (origin -1)
+        if (rd >= 0 && rd < T::CD_ROWS) {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                const int idx = kPX * k - 3 + p;   // column -4 + 8k + p relative to origin -1
+                if (idx >= 0 && idx < T::CD_PITCH) {
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) sCD[co * T::CD_PLANE + rd * T::CD_PITCH + idx] = acc[p][co];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- S4: d = c * (value / pow(min(blur7x7(csum), 1), root)), in place          gaussian_regulator_tensor.py:34-36
+    for (int t = tid; t < T::CD_ROWS * T::D_RUNS; t += NT) {
+        const int r = t % T::CD_ROWS, k = t / T::CD_ROWS;
+        const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kPX * k;
+        if (gy < 0 || gy >= h) {   // outside the level: zero padding of the end convolution
+            f2 z[kPX];
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) z[p] = zero2();
+#pragma unroll
+            for (int co = 0; co < 3; ++co) store_cols8(sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k, z);
+            continue;
+        }
+        const bool row_ok = true;
+        f2 m[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) m[p] = zero2();
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            f2 v[14];
+            load_cols<7>(sCs + (r + ky) * T::CS_PITCH + kPX * k, v);
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) m[p] = fma2(P.wb[ky * 7 + kx], v[p + kx], m[p]);
+        }
+        bool all_unity = true;   // m >= 1 everywhere: the gain is exactly reg_value (the common case on textured input)
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) {
+            if (kPX * k + p - 1 > TW) m[p] = make_float2(1.0f, 1.0f);   // over-computed columns of the last run
+            all_unity = all_unity && (m[p].x >= 1.0f) && (m[p].y >= 1.0f);
+        }
+        f2 gain[kPX];
+        if (all_unity) {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) gain[p] = make_float2(P.reg_value, P.reg_value);
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p)   // rare path (flat / dark regions): calls one out-of-line copy of the pow code
+                gain[p] = make_float2(slow_gain(m[p].x, P.reg_value, P.reg_root), slow_gain(m[p].y, P.reg_value, P.reg_root));
+        }
+#pragma unroll
+        for (int co = 0; co < 3; ++co) {
+            f2 *cd = sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k;
+            f2 c[kPX];
+            {
+                const float4 *p4 = reinterpret_cast<const float4 *>(cd);
+#pragma unroll
+                for (int q = 0; q < kPX / 2; ++q) {
+                    const float4 tq = p4[q];
+                    c[2 * q] = make_float2(tq.x, tq.y);
+                    c[2 * q + 1] = make_float2(tq.z, tq.w);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                const int gx = gx0 + p;
+                c[p] = (row_ok && gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
+            }
+            store_cols8(cd, c);
+        }
+    }
+    __syncthreads();
+
+    // ---- orient output: central TH x TW of d, coalesced 128-bit NHWC stores (4 consecutive floats = (pixel, channel))
+    if (orient) {
+        const float *sCDf = reinterpret_cast<const float *>(sCD);
+        const bool vec_ok = (w % 4) == 0;
+        constexpr int QUADS = TW * 3 / 4;
+        for (int i = tid; i < 2 * TH * QUADS; i += NT) {
+            const int q = i % QUADS, rest = i / QUADS;
+            const int r = rest % TH, lane = rest / TH;
+            const int gy = ty0 + r;
+            if (gy >= h || (lane == 1 && !has_b)) continue;
+            float vals[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int f = 4 * q + e, px = f / 3, ch = f - 3 * px;
+                vals[e] = sCDf[2 * (ch * T::CD_PLANE + (r + 1) * T::CD_PITCH + px + 1) + lane];
+            }
+            float *dst = orient + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3 + 4 * q;
+            const int last_px = tx0 + (4 * q + 3) / 3;
+            if (vec_ok && last_px < w) {
+                *reinterpret_cast<float4 *>(dst) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (tx0 + (4 * q + e) / 3 < w) dst[e] = vals[e];
+            }
+        }
+    }
+
+    // ---- S5-S7: e = clip(relu(conv3x3(d, end))); p = mask * e; g = mean(p)                 recognition_testing.py:73-77
+    for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+        const int r = t % TH, k = t / TH;
+        const int gy = ty0 + r, gx0 = tx0 + kPX * k;
+        if (gy >= h || gx0 >= w) continue;
+        f2 acc[kPX][3];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                f2 v[10];
+                load_cols<5>(sCD + ci * T::CD_PLANE + (r + ky) * T::CD_PITCH + kPX * k, v);
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                        for (int co = 0; co < 3; ++co)
+                            acc[p][co] = fma2(P.w5[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+            }
+        }
+        const bool row_in = gy >= P.border && gy < h - P.border;
+        const bool all_keep = row_in && gx0 >= P.border && gx0 + kPX <= w - P.border;   // run clear of the border mask
+        const float third = __fdiv_rn(1.0f, 3.0f);
+        f2 g[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p)
+#pragma unroll
+            for (int co = 0; co < 3; ++co)
+                acc[p][co] = make_float2(clip_nan(relu_nan(acc[p][co].x), P.clip_max),
+                                         clip_nan(relu_nan(acc[p][co].y), P.clip_max));
+        if (!all_keep) {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                const int gx = gx0 + p;
+                if (row_in && gx >= P.border && gx < w - P.border) continue;
+#pragma unroll
+                for (int co = 0; co < 3; ++co) {   // pad_inwards multiplies by 0: NaN stays NaN
+                    const float a = acc[p][co].x, b = acc[p][co].y;
+                    acc[p][co] = make_float2(a != a ? a : 0.0f * a, b != b ? b : 0.0f * b);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < kPX; ++p)
+            g[p] = mul2(add2(add2(acc[p][0], acc[p][1]), acc[p][2]), make_float2(third, third));
+        const bool full = gx0 + kPX <= w;
+        const bool vec_ok = full && (w % 4) == 0;
+#pragma unroll
+        for (int lane = 0; lane < 2; ++lane) {
+            if (lane == 1 && !has_b) break;
+            const size_t pix = ((size_t)(lane ? img1 : img0) * h + gy) * w + gx0;
+            float vals[kPX * 3];
+#pragma unroll
+            for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                for (int co = 0; co < 3; ++co) vals[3 * p + co] = lane ? acc[p][co].y : acc[p][co].x;
+            if (line_end) {
+                float *dst = line_end + pix * 3;
+                if (vec_ok) {
+#pragma unroll
+                    for (int q = 0; q < kPX * 3 / 4; ++q)
+                        reinterpret_cast<float4 *>(dst)[q] =
+                            make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kPX * 3; ++e)
+                        if (gx0 + e / 3 < w) dst[e] = vals[e];
+                }
+            }
+            if (gray) {
+                float *dst = gray + pix;
+                if (vec_ok) {
+                    reinterpret_cast<float4 *>(dst)[0] = lane ? make_float4(g[0].y, g[1].y, g[2].y, g[3].y)
+                                                              : make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+                    reinterpret_cast<float4 *>(dst)[1] = lane ? make_float4(g[4].y, g[5].y, g[6].y, g[7].y)
+                                                              : make_float4(g[4].x, g[5].x, g[6].x, g[7].x);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p)
+                        if (gx0 + p < w) dst[p] = lane ? g[p].y : g[p].x;
+                }
+            }
+        }
+        if (P.win.count) {
+            // run maximum per image as ordered ints: values are >= 0, NaN maps to 0x7fc00000 which beats everything
+            int best[2] = {0, 0};
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                if (gx0 + p < w) {
+                    const int a = g[p].x != g[p].x ? 0x7fc00000 : __float_as_int(g[p].x);
+                    const int b = g[p].y != g[p].y ? 0x7fc00000 : __float_as_int(g[p].y);
+                    best[0] = max(best[0], a);
+                    best[1] = max(best[1], b);
+                }
+            }
+            const int nwy = P.win.count / P.win.ow;
+            for (int i = 0; i < nwy; ++i) {
+                if (gy < P.win.y0[i] || gy >= P.win.y1[i]) continue;
+                for (int j = 0; j < P.win.ow; ++j) {
+                    if (gx0 < P.win.x0[j] || gx0 >= P.win.x1[j]) continue;   // bounds are multiples of 8: whole run
+                    atomicMax(&sWin[i * P.win.ow + j], best[0]);
+                    atomicMax(&sWin[4 + i * P.win.ow + j], best[1]);
+                }
+            }
+        }
+    }
+    if (P.win.count) {
+        __syncthreads();
+        if (tid < 8) {
+            const int lane = tid >> 2, win = tid & 3;
+            if (win < P.win.count && (lane == 0 || has_b) && sWin[tid] != 0)
+                atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], sWin[tid]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+
+static bool bits_equal(float a, float b) { return std::memcmp(&a, &b, 4) == 0; }
+static f2 dup(float v) { return make_float2(v, v); }
+
+struct StackPlanHost {
+    ParamsA a;
+    ParamsB b;
+    bool s1_depthwise, s2_rgby;
+};
+
+// Validate the structure the fused kernels rely on and repack the HWIO filters as (w, w) pairs.
+int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackPlanHost *S)
 {
     if (!W) return fail(SILENT_E_INVAL, "null weights");
+    if (W->border < 0) return fail(SILENT_E_INVAL, "border must be >= 0");
+    S->s1_depthwise = S->s2_rgby = true;
     for (int t = 0; t < 9; ++t)
         for (int ci = 0; ci < 3; ++ci)
             for (int co = 0; co < 3; ++co) {
-                P->w1[t][ci][co] = W->rgc[(t * 3 + ci) * 3 + co];
-                P->w2[t][ci][co] = W->rgby[(t * 3 + ci) * 3 + co];
-                P->w5[t][ci][co] = W->end[(t * 3 + ci) * 3 + co];
-                if (!bits_equal(W->stripe[(t * 3 + ci) * 3 + co], W->stripe[(t * 3) * 3 + co]))
+                const int i = (t * 3 + ci) * 3 + co;
+                S->a.w1[t][ci][co] = dup(W->rgc[i]);
+                S->a.w2[t][ci][co] = dup(W->rgby[i]);
+                S->b.w5[t][ci][co] = dup(W->end[i]);
+                if (ci != co && W->rgc[i] != 0.0f) S->s1_depthwise = false;
+                if (!rgby_nonzero(t, ci, co) && W->rgby[i] != 0.0f) S->s2_rgby = false;
+                if (!bits_equal(W->stripe[i], W->stripe[(t * 3) * 3 + co]))
                     return fail(SILENT_E_STRUCTURE, "stripe filter differs across input channels at tap %d; the fused "
                                                     "stack needs identical input slices (use the per-operator calls)", t);
-                P->w3[t][co] = W->stripe[(t * 3) * 3 + co];
+                S->b.w3[t][co] = dup(W->stripe[(t * 3) * 3 + co]);
             }
     for (int t = 0; t < 49; ++t) {
         for (int s = 0; s < 9; ++s)
             if (!bits_equal(W->blur[t * 9 + s], W->blur[t * 9]))
                 return fail(SILENT_E_STRUCTURE, "blur filter slices differ at tap %d; the fused stack needs one 7x7 "
                                                 "kernel in every slice (use the per-operator calls)", t);
-        P->wb[t] = W->blur[t * 9];
+        S->b.wb[t] = dup(W->blur[t * 9]);
     }
-    if (W->border < 0) return fail(SILENT_E_INVAL, "border must be >= 0");
-    P->reg_value = W->regulation_value;
-    P->reg_root = W->regulation_root;
-    P->clip_max = W->clip_max;
-    P->border = W->border;
-    P->h = h;
-    P->w = w;
+    S->a.h = S->b.h = h;
+    S->a.w = S->b.w = w;
+    S->a.n = S->b.n = n;
+    S->b.reg_value = W->regulation_value;
+    S->b.reg_root = W->regulation_root;
+    S->b.clip_max = W->clip_max;
+    S->b.border = W->border;
+    S->b.win = WindowGeom();
     return SILENT_OK;
 }
 
-int stack_fused(const float *pyr, int n, int h, int w, const silent_stack_weights *W, float *orient, float *line_end,
-                float *gray, cudaStream_t stream)
+constexpr int kTileHA = 16, kTileHB = 32, kTileW = 64, kThreadsA = 128, kThreadsB = 256;
+
+template <bool DW, bool RGBY, bool PAIRED>
+static int launch_a(const void *pyr, const ParamsA &P, f2 *bsum2, dim3 grid, cudaStream_t stream)
+{
+    using T = TileA<kTileHA, kTileW>;
+    auto kern = stack_a_kernel<kTileHA, kTileW, kThreadsA, DW, RGBY, PAIRED>;
+    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
+    kern<<<grid, kThreadsA, T::kSmemBytes, stream>>>(pyr, P, bsum2);
+    SILENT_LAUNCH_CHECK("stack_a_kernel");
+    return SILENT_OK;
+}
+
+// room for one float2 plane per image pair (n images pair up into at most (n + levels) / 2 pairs for any pairing)
+size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * w * sizeof(f2) + 256; }
+
+// winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
+template <bool PAIRED>
+static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, f2 *bsum2, dim3 grid, cudaStream_t stream)
+{
+    if (dw && rgby) return launch_a<true, true, PAIRED>(in, P, bsum2, grid, stream);
+    if (dw) return launch_a<true, false, PAIRED>(in, P, bsum2, grid, stream);
+    if (rgby) return launch_a<false, true, PAIRED>(in, P, bsum2, grid, stream);
+    return launch_a<false, false, PAIRED>(in, P, bsum2, grid, stream);
+}
+
+// pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
+// tensor of pyramid_pair_kernel with `pair_levels` levels per frame (images paired across consecutive frames).
+int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
+                float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
+                int *winmax, cudaStream_t stream)
 {
     if (!pyr) return fail(SILENT_E_INVAL, "silent_stack_fused: null pyramid");
     if (n <= 0 || h <= 0 || w <= 0) return fail(SILENT_E_INVAL, "silent_stack_fused: bad shape %dx%dx%d", n, h, w);
-    if (n > 65535) return fail(SILENT_E_SHAPE, "silent_stack_fused: at most 65535 levels per call");
-    StackParams P;
-    int rc = pack_stack_params(W, h, w, &P);
+    const bool paired_in = pair_levels > 0;
+    const int levels = paired_in ? pair_levels : 1;
+    if (n % levels != 0) return fail(SILENT_E_INVAL, "silent_stack_fused: n must be a multiple of the levels per frame");
+    const int pairs = ((n / levels + 1) / 2) * levels;
+    if (pairs > 65535) return fail(SILENT_E_SHAPE, "silent_stack_fused: at most 65535 image pairs per call");
+    if (!workspace || workspace_bytes < stack_workspace_bytes(n, h, w))
+        return fail(SILENT_E_CAPACITY, "silent_stack_fused: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                    stack_workspace_bytes(n, h, w));
+    for (const void *p : {(const void *)pyr, (const void *)orient, (const void *)line_end, (const void *)gray})
+        if (((uintptr_t)p & 15) != 0) return fail(SILENT_E_INVAL, "silent_stack_fused: tensors must be 16-byte aligned");
+    StackPlanHost S;
+    int rc = pack_stack_params(W, n, h, w, &S);
     if (rc != SILENT_OK) return rc;
-    constexpr int TH = 32, TW = 64;
-    using T = StackTile<TH, TW>;
-    static bool configured = false;
-    if (!configured) {
-        SILENT_CUDA(cudaFuncSetAttribute(stack_fused_kernel<TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)T::kSmemBytes));
-        configured = true;
-    }
-    dim3 grid(ceil_div(w, TW), ceil_div(h, TH), n);
-    stack_fused_kernel<TH, TW><<<grid, kStackThreads, T::kSmemBytes, stream>>>(pyr, P, orient, line_end, gray);
-    SILENT_LAUNCH_CHECK("stack_fused_kernel");
+    if (geo && winmax) S.b.win = *geo;
+    S.a.pair_levels = S.b.pair_levels = levels;
+    f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const dim3 grid_a(ceil_div(w, kTileW), ceil_div(h, kTileHA), pairs);
+    const dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileHB), pairs);
+    rc = paired_in ? dispatch_a<true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, bsum2, grid_a, stream)
+                   : dispatch_a<false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, bsum2, grid_a, stream);
+    if (rc != SILENT_OK) return rc;
+    using TB = TileB<kTileHB, kTileW>;
+    auto kern = stack_b_kernel<kTileHB, kTileW, kThreadsB>;
+    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
+    kern<<<grid, kThreadsB, TB::kSmemBytes, stream>>>(bsum2, S.b, orient, line_end, gray, winmax);
+    SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
 
 }  // namespace silent
 
-extern "C" int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const silent_stack_weights *weights_host,
-                                  float *orient_dev, float *line_end_dev, float *gray_dev, silent_stream stream)
+extern "C" {
+
+size_t silent_stack_workspace_bytes(int n, int h, int w)
 {
-    return silent::stack_fused(pyramid_dev, n, h, w, weights_host, orient_dev, line_end_dev, gray_dev,
-                               (cudaStream_t)stream);
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return silent::stack_workspace_bytes(n, h, w);
 }
+
+int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const silent_stack_weights *weights_host,
+                       float *orient_dev, float *line_end_dev, float *gray_dev, void *workspace_dev,
+                       size_t workspace_bytes, silent_stream stream)
+{
+    return silent::stack_fused(pyramid_dev, n, h, w, 0, weights_host, orient_dev, line_end_dev, gray_dev, workspace_dev,
+                               workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -93,7 +93,9 @@ def test_argument_validation_without_gpu(built_lib):
     assert L.silent_conv2d(ctypes.c_void_p(8), 1, 4, 4, 9, ctypes.c_void_p(8), 3, 3, 0, 0.0, ctypes.c_void_p(8), None) == -2
     assert L.silent_selection_workspace_bytes(0, 4, 4) == 0 and L.silent_selection_workspace_bytes(6, 192, 288) > 0
     w = _lib.SilentStackWeights()
-    assert L.silent_stack_fused(None, 1, 4, 4, ctypes.byref(w), None, None, None, None) == -1
+    assert L.silent_stack_fused(None, 1, 4, 4, ctypes.byref(w), None, None, None, None, 0, None) == -1
+    assert L.silent_stack_workspace_bytes(6, 192, 288) >= 3 * 192 * 288 * 8 and L.silent_stack_workspace_bytes(0, 1, 1) == 0
+    assert L.silent_stack_fused(ctypes.c_void_p(16), 2, 4, 4, ctypes.byref(w), None, None, None, None, 0, None) == -3
     assert L.silent_launch_count() >= 0
 
 
@@ -103,7 +105,8 @@ def test_fused_stack_structure_check_is_host_side(built_lib):
     blur = f["blur"].copy()
     blur[3, 3, 1, 2] *= 2
     w = _lib.make_stack_weights(f["rgc"], f["rgby"], f["stripe"], blur, f["end"])
-    rc = built_lib.silent_stack_fused(ctypes.c_void_p(8), 1, 4, 4, ctypes.byref(w), None, None, None, None)
+    rc = built_lib.silent_stack_fused(ctypes.c_void_p(16), 1, 4, 4, ctypes.byref(w), None, None, None,
+                                      ctypes.c_void_p(256), 1 << 20, None)
     assert rc == -5 and b"blur filter slices differ" in built_lib.silent_last_error()
     with pytest.raises(ValueError):
         _lib.make_stack_weights(f["rgc"], f["rgby"], f["stripe"], f["blur"][:5, :5], f["end"])
