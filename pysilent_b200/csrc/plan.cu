@@ -182,8 +182,8 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 continue;
             }
             const int byte_lo = lo * p->frame_c, byte_hi = (hi + 1) * p->frame_c;
-            pl.word_lo[t] = byte_lo / 4;
-            pl.nwords[t] = (byte_hi + 3) / 4 - pl.word_lo[t];
+            pl.word_lo[t] = (byte_lo / 16) * 4;                       // 128-bit aligned span, in 32-bit words
+            pl.nwords[t] = ((byte_hi + 15) / 16) * 4 - pl.word_lo[t];
             widest = std::max(widest, pl.nwords[t]);
         }
         pl.vpitch = 4 * widest;

@@ -165,30 +165,41 @@ __global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid
     }
     __syncthreads();
 
-    // ---- phase V: column sums over the 6 y-taps, 4 byte-columns (one aligned word) per task ---------------------------
-    const int nw = P.nwords[bx], wlo = P.word_lo[bx];
+    // ---- phase V: column sums over the 6 y-taps, 16 byte-columns (one aligned 128-bit load per tap row and frame) per
+    //      task: 12 independent 16-byte loads in flight per thread cover the HBM/L2 latency ---------------------------
+    const int nw = P.nwords[bx], wlo = P.word_lo[bx];   // multiples of 4 words
+    const int nq = nw >> 2;
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
-    for (int t = tid; t < th * nw; t += kPairThreads) {
-        const int r = t / nw, wi = t - r * nw;
-        f2 acc[4];
-        acc[0] = acc[1] = acc[2] = acc[3] = make_float2(0.0f, 0.0f);
+    for (int t = tid; t < th * nq; t += kPairThreads) {
+        const int r = t / nq, qi = t - r * nq;
+        f2 acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
         if (sTy[r * kTaps] >= 0) {
+            uint4 qa[kTaps], qb[kTaps];
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
                 const size_t off = (size_t)sTy[r * kTaps + j] * P.row_bytes;
-                const uint32_t wa = __ldg(reinterpret_cast<const uint32_t *>(frameA + off) + wlo + wi);
-                const uint32_t wb = __ldg(reinterpret_cast<const uint32_t *>(frameB + off) + wlo + wi);
+                qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + off) + (wlo >> 2) + qi);
+                qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + off) + (wlo >> 2) + qi);
+            }
+#pragma unroll
+            for (int j = 0; j < kTaps; ++j) {
                 const float wy = sWy[r * kTaps + j];
                 const f2 wy2 = make_float2(wy, wy);
-                acc[0] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa, 0x7440), magic_byte(wb, 0x7440)), bias), acc[0]);
-                acc[1] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa, 0x7441), magic_byte(wb, 0x7441)), bias), acc[1]);
-                acc[2] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa, 0x7442), magic_byte(wb, 0x7442)), bias), acc[2]);
-                acc[3] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa, 0x7443), magic_byte(wb, 0x7443)), bias), acc[3]);
+                const uint32_t wa[4] = {qa[j].x, qa[j].y, qa[j].z, qa[j].w}, wb[4] = {qb[j].x, qb[j].y, qb[j].z, qb[j].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc[4 * k + 0] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7440), magic_byte(wb[k], 0x7440)), bias), acc[4 * k + 0]);
+                    acc[4 * k + 1] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7441), magic_byte(wb[k], 0x7441)), bias), acc[4 * k + 1]);
+                    acc[4 * k + 2] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7442), magic_byte(wb[k], 0x7442)), bias), acc[4 * k + 2]);
+                    acc[4 * k + 3] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7443), magic_byte(wb[k], 0x7443)), bias), acc[4 * k + 3]);
+                }
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * P.vpitch + 4 * wi);
-        dst[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-        dst[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * P.vpitch + 16 * qi);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
     }
     __syncthreads();
 
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid
 bool pyramid_pair_supported(const silent_plan *plan)
 {
     const silent_params &p = plan->params;
-    return plan->on_device && p.frame_dtype == SILENT_U8 && p.num_colors == 3 && (p.frame_w * p.frame_c) % 4 == 0 &&
+    return plan->on_device && p.frame_dtype == SILENT_U8 && p.num_colors == 3 && (p.frame_w * p.frame_c) % 16 == 0 &&
            plan->pair_ok;
 }
 
@@ -240,7 +251,7 @@ size_t pyramid_pair_bytes(const silent_plan *plan, int batch)
 int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream)
 {
     if (!pyramid_pair_supported(plan)) return fail(SILENT_E_SHAPE, "frame-pair pyramid kernel does not support this plan");
-    if (((uintptr_t)frames_dev & 3) != 0) return fail(SILENT_E_INVAL, "frames must be 4-byte aligned");
+    if (((uintptr_t)frames_dev & 15) != 0) return fail(SILENT_E_INVAL, "frames must be 16-byte aligned");
     const silent_params &p = plan->params;
     const int pairs = (batch + 1) / 2;
     if (pairs > 65535) return fail(SILENT_E_SHAPE, "at most 131070 frames per call");

@@ -19,6 +19,8 @@
 //    host and compiled out (dense variants exist for arbitrary weights).
 // Evaluation order = canonical order of oracle/silent_oracle.c (chains in (ky, ci, kx) order), so results are
 // bit-identical to it. HBM-bound by design; tensor cores do not apply (3-channel fp32 stencils).
+#include <cuda.h>
+
 #include <cstring>
 #include <initializer_list>
 
@@ -52,6 +54,35 @@ __device__ __noinline__ float slow_gain(float m, float value, float root) { retu
 
 constexpr int kPX = 8;   // pixels per thread run
 
+// ---- TMA (cp.async.bulk.tensor) tile loads: one elected thread issues a 3-D box copy global -> shared; the hardware
+//      zero-fills everything outside the tensor, which is exactly the SAME padding of the first convolution of a kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_box3(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar,
+                                              uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
 // smallest pitch (in float2) >= n whose byte stride is an odd multiple of 16: conflict-free 128-bit row-strided access
 constexpr int round_pitch(int n) { return n + ((2 - n % 4) + 4) % 4; }
 
@@ -83,6 +114,7 @@ struct ParamsA {
     f2 w2[9][3][3];   // rgby
     int h, w, n;      // level shape, number of images
     int pair_levels;  // image pairing: pair p holds images (a, a + pair_levels), see pair_images()
+    int use_tma;      // PAIRED_IN only: load the tile with one TMA box copy
 };
 
 // Which two images ride in the float2 lanes of pair p. With pair_levels = 1 these are images (2p, 2p + 1); the
@@ -120,10 +152,11 @@ __host__ __device__ constexpr bool rgby_nonzero(int tap, int ci, int co)
 // planes); otherwise it is an NHWC float32 pyramid [n][h][w][3] (stand-alone silent_stack_fused).
 template <int TH, int TW, int NT, bool S1_DEPTHWISE, bool S2_RGBY, bool PAIRED_IN>
 __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ input, const __grid_constant__ ParamsA P,
-                                                     f2 *__restrict__ bsum2)
+                                                     const __grid_constant__ CUtensorMap tmap, f2 *__restrict__ bsum2)
 {
     using T = TileA<TH, TW>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t tma_bar;
     f2 *sX = reinterpret_cast<f2 *>(smem_raw);   // [3][X_ROWS][X_PITCH]
     f2 *sA = sX + 3 * T::X_PLANE;                // [3][A_ROWS][A_PITCH]
 
@@ -135,8 +168,15 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
     bool has_b;
     pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
 
-    if (PAIRED_IN) {
-        // ---- load x: the planes are already pair-interleaved: 128-bit = 2 pixels x 2 frames, zero outside the level ----
+    if (PAIRED_IN && P.use_tma) {
+        // ---- load x: the planes are already pair-interleaved; one TMA box [3 planes][X_ROWS][X_PITCH] -------------------
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0)
+            tma_load_box3(sX, &tmap, 2 * (tx0 - 2), ty0 - 2, 3 * pair, &tma_bar, (uint32_t)(3 * T::X_PLANE * sizeof(f2)));
+        mbar_wait(&tma_bar, 0);
+    } else if (PAIRED_IN) {
+        // ---- same tile with plain 128-bit loads (= 2 pixels x 2 frames), zero outside the level ------------------------
         constexpr int QUADS = T::X_PITCH / 2;
         const f2 *src = reinterpret_cast<const f2 *>(input) + (size_t)pair * 3 * h * w;
         const bool vec_ok = (w % 2) == 0;
@@ -273,14 +313,14 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
 #pragma unroll
         for (int p = 0; p < kPX; ++p)
             s[p] = add2(add2(relu2_finite(acc[p][0]), relu2_finite(acc[p][1])), relu2_finite(acc[p][2]));
-        f2 *dst = bsum2 + ((size_t)pair * h + gy) * w + gx0;
-        if (gx0 + kPX <= w && (w % 2) == 0) {
-            store_cols8(dst, s);
-        } else {
+        // rows of bsum2 are w + 2 wide: pixel x lives in column x + 1 between two zero columns, so that stack_b's tile
+        // origin (x - 5) is an even column = a 16-byte aligned TMA box start
+        f2 *dst = bsum2 + ((size_t)pair * h + gy) * (w + 2) + gx0 + 1;
 #pragma unroll
-            for (int p = 0; p < kPX; ++p)
-                if (gx0 + p < w) dst[p] = s[p];
-        }
+        for (int p = 0; p < kPX; ++p)
+            if (gx0 + p < w) dst[p] = s[p];
+        if (gx0 == 0) dst[-1] = zero2();
+        if (gx0 + kPX >= w) dst[w - gx0] = zero2();
     }
 }
 
@@ -296,6 +336,7 @@ struct ParamsB {
     int border;
     int h, w, n;
     int pair_levels;  // see pair_images()
+    int use_tma;      // load the channel-sum tile with one TMA box copy
     WindowGeom win;   // fused region maxima (stack.h)
 };
 
@@ -317,11 +358,13 @@ struct TileB {
 
 template <int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
-                                                     float *__restrict__ orient, float *__restrict__ line_end,
-                                                     float *__restrict__ gray, int *__restrict__ winmax)
+                                                     const __grid_constant__ CUtensorMap tmap, float *__restrict__ orient,
+                                                     float *__restrict__ line_end, float *__restrict__ gray,
+                                                     int *__restrict__ winmax)
 {
     using T = TileB<TH, TW>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t tma_bar;
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
     f2 *sCD = sCs + T::CS_PLANE;                 // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
@@ -337,10 +380,16 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
 
     if (tid < 8) sWin[tid] = 0;
 
-    // ---- load the channel-sum tile (pairs are already interleaved): 128-bit = 2 pixels x 2 images --------------------
-    {
+    // ---- load the channel-sum tile (pairs are already interleaved): one TMA box [B_ROWS][B_PITCH], zero outside -------
+    if (P.use_tma) {
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0)
+            tma_load_box3(sB, &tmap, 2 * (tx0 - 4), ty0 - 5, pair, &tma_bar, (uint32_t)(T::B_PLANE * sizeof(f2)));
+        mbar_wait(&tma_bar, 0);
+    } else {
         constexpr int QUADS = T::B_PITCH / 2;
-        const f2 *src = bsum2 + (size_t)pair * h * w;
+        const f2 *src = bsum2 + (size_t)pair * h * (w + 2) + 1;   // pixel x is stored in column x + 1
         const bool vec_ok = (w % 2) == 0;
         for (int i = tid; i < T::B_ROWS * QUADS; i += NT) {
             const int q = i % QUADS, r = i / QUADS;
@@ -348,8 +397,8 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
             float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const int x0 = tx0 - 5 + 2 * q, x1 = x0 + 1;   // plane column 2q <-> level column tx0 - 5 + 2q
             if (gy >= 0 && gy < h) {
-                const f2 *row = src + (size_t)gy * w;
-                if (vec_ok && (x0 & 1) == 0 && x0 >= 0 && x1 < w) {
+                const f2 *row = src + (size_t)gy * (w + 2);
+                if (vec_ok && x0 >= 0 && x1 < w) {   // x0 is odd, so column x0 + 1 is even: 16-byte aligned
                     v = __ldg(reinterpret_cast<const float4 *>(row + x0));
                 } else {
                     if (x0 >= 0 && x0 < w) {
@@ -626,6 +675,34 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
 // ---------------------------------------------------------------------------------------------------------------------
 
 static bool bits_equal(float a, float b) { return std::memcmp(&a, &b, 4) == 0; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// float32 view [planes][rows][2 * w] of a pair-interleaved tensor, boxes of [bp][br][2 * pitch]. False if TMA cannot be used.
+static bool make_pair_map(CUtensorMap *map, const void *base, int w, int rows, long long planes, int pitch, int box_rows,
+                          int box_planes)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    if ((w % 2) != 0 || 2 * pitch > 256 || box_rows > 256 || ((uintptr_t)base & 15) != 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * w, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)2 * w * 4, (cuuint64_t)2 * w * 4 * rows};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * pitch), (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static f2 dup(float v) { return make_float2(v, v); }
 
 struct StackPlanHost {
@@ -675,27 +752,28 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
 constexpr int kTileHA = 16, kTileHB = 32, kTileW = 64, kThreadsA = 128, kThreadsB = 256;
 
 template <bool DW, bool RGBY, bool PAIRED>
-static int launch_a(const void *pyr, const ParamsA &P, f2 *bsum2, dim3 grid, cudaStream_t stream)
+static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, dim3 grid, cudaStream_t stream)
 {
     using T = TileA<kTileHA, kTileW>;
     auto kern = stack_a_kernel<kTileHA, kTileW, kThreadsA, DW, RGBY, PAIRED>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
-    kern<<<grid, kThreadsA, T::kSmemBytes, stream>>>(pyr, P, bsum2);
+    kern<<<grid, kThreadsA, T::kSmemBytes, stream>>>(pyr, P, tmap, bsum2);
     SILENT_LAUNCH_CHECK("stack_a_kernel");
     return SILENT_OK;
 }
 
 // room for one float2 plane per image pair (n images pair up into at most (n + levels) / 2 pairs for any pairing)
-size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * w * sizeof(f2) + 256; }
+size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 256; }
 
 // winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
 template <bool PAIRED>
-static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, f2 *bsum2, dim3 grid, cudaStream_t stream)
+static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, dim3 grid,
+                      cudaStream_t stream)
 {
-    if (dw && rgby) return launch_a<true, true, PAIRED>(in, P, bsum2, grid, stream);
-    if (dw) return launch_a<true, false, PAIRED>(in, P, bsum2, grid, stream);
-    if (rgby) return launch_a<false, true, PAIRED>(in, P, bsum2, grid, stream);
-    return launch_a<false, false, PAIRED>(in, P, bsum2, grid, stream);
+    if (dw && rgby) return launch_a<true, true, PAIRED>(in, P, tmap, bsum2, grid, stream);
+    if (dw) return launch_a<true, false, PAIRED>(in, P, tmap, bsum2, grid, stream);
+    if (rgby) return launch_a<false, true, PAIRED>(in, P, tmap, bsum2, grid, stream);
+    return launch_a<false, false, PAIRED>(in, P, tmap, bsum2, grid, stream);
 }
 
 // pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
@@ -724,13 +802,19 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     const dim3 grid_a(ceil_div(w, kTileW), ceil_div(h, kTileHA), pairs);
     const dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileHB), pairs);
-    rc = paired_in ? dispatch_a<true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, bsum2, grid_a, stream)
-                   : dispatch_a<false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, bsum2, grid_a, stream);
+    CUtensorMap map_x, map_b;
+    std::memset(&map_x, 0, sizeof(map_x));
+    std::memset(&map_b, 0, sizeof(map_b));
+    using TA = TileA<kTileHA, kTileW>;
+    S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
+    rc = paired_in ? dispatch_a<true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, grid_a, stream)
+                   : dispatch_a<false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, grid_a, stream);
     if (rc != SILENT_OK) return rc;
     using TB = TileB<kTileHB, kTileW>;
     auto kern = stack_b_kernel<kTileHB, kTileW, kThreadsB>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
-    kern<<<grid, kThreadsB, TB::kSmemBytes, stream>>>(bsum2, S.b, orient, line_end, gray, winmax);
+    S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
+    kern<<<grid, kThreadsB, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
