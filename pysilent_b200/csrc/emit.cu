@@ -68,40 +68,91 @@ __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict
 }
 
 // One warp per row (level, y). Pass 0 counts hits, pass 1 writes them at row_offset in x order.
-template <bool WRITE>
-__global__ void __launch_bounds__(256) emit_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
-                                                        const float *__restrict__ pooled, int *__restrict__ row_count,
-                                                        const long long *__restrict__ row_offset,
-                                                        long long *__restrict__ points, long long capacity)
+// COUNT pass: one warp per row (level, y); 128-bit loads when the row length allows; writes the row's hit count.
+__global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
+                                                         const float *__restrict__ pooled, int *__restrict__ row_count)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const int n = row / h, y = row % h;
+    const int n = row / h, y = row - n * h;
     const float *v = value + (size_t)row * w;
     const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
-    long long base = WRITE ? row_offset[row] : 0;
-    int total = 0;
+    int hits = 0;
+    if ((w & 3) == 0) {
+        for (int q = lane; q < (w >> 2); q += 32) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(v) + q);
+            const int x = 4 * q;
+            hits += (f.x >= __ldg(pool_row + nearest_src(x, g.sx, g.ow))) + (f.y >= __ldg(pool_row + nearest_src(x + 1, g.sx, g.ow))) +
+                    (f.z >= __ldg(pool_row + nearest_src(x + 2, g.sx, g.ow))) + (f.w >= __ldg(pool_row + nearest_src(x + 3, g.sx, g.ow)));
+        }
+    } else {
+        for (int x = lane; x < w; x += 32) hits += __ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow));
+    }
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if (lane == 0) row_count[row] = hits;
+}
+
+// One CTA per level: exclusive scan of the level's row counts -> row_offset (within the level, in place) + level_total.
+__global__ void __launch_bounds__(256) scan_level_kernel(int *__restrict__ row_count, int h, int *__restrict__ level_total)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    int *rows = row_count + (size_t)blockIdx.x * h;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < h; base += 256) {
+        const int i = base + threadIdx.x;
+        const int mine = i < h ? rows[i] : 0;
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = s_carry + incl - mine;
+        for (int k = 0; k < warp; ++k) before += s_warp[k];
+        if (i < h) rows[i] = before | (mine ? 0x40000000 : 0);   // bit 30 flags rows that have hits (counts < 2^30)
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = before + mine;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) level_total[blockIdx.x] = s_carry;
+}
+
+// WRITE pass: one warp per row; rows without hits (the vast majority) return at once. Hits are written in x order at
+// level_offset[level] + row_offset[row], i.e. in tf.where's row-major order.
+__global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
+                                                         const float *__restrict__ pooled, const int *__restrict__ row_offset,
+                                                         const long long *__restrict__ level_offset,
+                                                         long long *__restrict__ points, long long capacity)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int packed = __ldg(row_offset + row);
+    if (!(packed & 0x40000000)) return;
+    const int n = row / h, y = row - n * h;
+    const float *v = value + (size_t)row * w;
+    const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
+    long long base = __ldg(level_offset + n) + (packed & 0x3fffffff);
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
         bool hit = false;
         if (x < w) hit = __ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow));
         const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-        if (WRITE) {
-            if (hit) {
-                const long long slot = base + __popc(ballot & ((1u << lane) - 1u));
-                if (slot < capacity) {
-                    longlong2 a = make_longlong2(n, y), b = make_longlong2(x, 0);
-                    reinterpret_cast<longlong2 *>(points)[slot * 2] = a;
-                    reinterpret_cast<longlong2 *>(points)[slot * 2 + 1] = b;
-                }
+        if (hit) {
+            const long long slot = base + __popc(ballot & ((1u << lane) - 1u));
+            if (slot < capacity) {
+                longlong2 a = make_longlong2(n, y), b = make_longlong2(x, 0);
+                reinterpret_cast<longlong2 *>(points)[slot * 2] = a;
+                reinterpret_cast<longlong2 *>(points)[slot * 2 + 1] = b;
             }
-            base += __popc(ballot);
-        } else {
-            total += __popc(ballot);
         }
+        base += __popc(ballot);
     }
-    if (!WRITE && lane == 0) row_count[row] = total;
 }
 
 // Single-CTA exclusive scan of the per-row counts (rows = levels * h, at most a few hundred thousand).
@@ -190,7 +241,7 @@ size_t selection_bytes(int n, int h, int w)
     const size_t rows = (size_t)n * h;
     (void)w;
     return align_up((size_t)n * 4096 * sizeof(float), 256) + align_up(rows * sizeof(int), 256) +
-           align_up(rows * sizeof(long long), 256) + 256;
+           align_up((size_t)n * sizeof(long long), 256) + align_up((size_t)n * sizeof(int), 256) + 256;
 }
 
 // True when the pooling windows of max_value_indices_region can be reduced inside stack_b_kernel.
@@ -234,9 +285,11 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     char *ws = (char *)workspace;
     float *pooled = (float *)ws;
     ws += align_up((size_t)n * 4096 * sizeof(float), 256);
-    int *row_count = (int *)ws;
+    int *row_offset = (int *)ws;            // offset of each row within its level
     ws += align_up((size_t)rows * sizeof(int), 256);
-    long long *row_offset = (long long *)ws;
+    long long *level_offset = (long long *)ws;
+    ws += align_up((size_t)n * sizeof(long long), 256);
+    int *level_total = (int *)ws;
 
     if (fused_winmax) {
         // the stack kernel already reduced the per-region maxima (ordered-int encoding == float bits, NaN = 0x7fc00000)
@@ -245,16 +298,18 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
         window_max_kernel<<<dim3(g.oh * g.ow, n), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
         SILENT_LAUNCH_CHECK("window_max_kernel");
     }
-    const int warps_per_block = 8;
-    const unsigned blocks = (unsigned)ceil_div(rows, warps_per_block);
-    emit_rows_kernel<false><<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_count, nullptr, nullptr, 0);
-    SILENT_LAUNCH_CHECK("emit_rows_kernel<count>");
-    scan_rows_kernel<<<1, 1024, 0, stream>>>(row_count, rows, row_offset, (long long *)count);
+    if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
+    const unsigned blocks = (unsigned)ceil_div(rows, 8);
+    count_rows_kernel<<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_offset);
+    SILENT_LAUNCH_CHECK("count_rows_kernel");
+    scan_level_kernel<<<n, 256, 0, stream>>>(row_offset, h, level_total);
+    SILENT_LAUNCH_CHECK("scan_level_kernel");
+    scan_rows_kernel<<<1, 1024, 0, stream>>>(level_total, n, level_offset, (long long *)count);
     SILENT_LAUNCH_CHECK("scan_rows_kernel");
     if (capacity > 0) {
-        emit_rows_kernel<true><<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, nullptr, row_offset,
-                                                           (long long *)points, (long long)capacity);
-        SILENT_LAUNCH_CHECK("emit_rows_kernel<write>");
+        write_rows_kernel<<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_offset, level_offset,
+                                                      (long long *)points, (long long)capacity);
+        SILENT_LAUNCH_CHECK("write_rows_kernel");
     }
     return SILENT_OK;
 }

@@ -123,6 +123,7 @@ int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, fl
 
 typedef float2 f2;
 constexpr int kPairThreads = 256;
+constexpr int kVGroup = 18;   // float2 slots per group of 16 byte-columns in the column-sum buffer (16 + 2 of padding)
 
 struct PairParams {
     const uint8_t *frames;
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid
                 }
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * P.vpitch + 16 * qi);
+        // 16 columns = 128 B per task: padded to 144 B so consecutive lanes start in consecutive 16-byte bank groups
+        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * P.vpitch + kVGroup * qi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) dst[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
     }
@@ -228,7 +230,10 @@ __global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid
             f2 acc = make_float2(0.0f, 0.0f);
             if (col_ok) {
 #pragma unroll
-                for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[bc[i] + c], acc);
+                for (int i = 0; i < kTaps; ++i) {
+                    const int b = bc[i] + c;
+                    acc = __ffma2_rn(wx[i], row[b + (kVGroup - 16) * (b >> 4)], acc);
+                }
             }
             out[c * plane + (size_t)oy * w] = acc;
         }
