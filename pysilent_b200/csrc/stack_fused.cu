@@ -98,6 +98,53 @@ __device__ __forceinline__ void load_cols(const f2 *__restrict__ src, f2 (&v)[2 
     }
 }
 
+// 8 pixels x 3 channels of one lane of the pair as NHWC floats: six 128-bit stores (96 contiguous bytes)
+template <int LANE>
+__device__ __forceinline__ void store_nhwc8(float *__restrict__ dst, const f2 (&v)[kPX][3], bool vec_ok, int valid_px)
+{
+    float vals[kPX * 3];
+#pragma unroll
+    for (int p = 0; p < kPX; ++p)
+#pragma unroll
+        for (int co = 0; co < 3; ++co) vals[3 * p + co] = LANE ? v[p][co].y : v[p][co].x;
+    if (vec_ok) {
+#pragma unroll
+        for (int q = 0; q < kPX * 3 / 4; ++q)
+            reinterpret_cast<float4 *>(dst)[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < kPX * 3; ++e)
+            if (e / 3 < valid_px) dst[e] = vals[e];
+    }
+}
+
+// Write a staged tile ([2 images][TH][TW*3 (+4 pad)] floats, NHWC) to global memory with coalesced 128-bit stores.
+template <int TH, int TW, int NT>
+__device__ __forceinline__ void copy_out_tile(const float *__restrict__ stage, float *__restrict__ out, int img0, int img1,
+                                              bool has_b, int ty0, int tx0, int h, int w, int tid)
+{
+    if (!out) return;
+    constexpr int QUADS = TW * 3 / 4, PITCH = TW * 3 + 4;
+    const int valid_floats = min(TW, w - tx0) * 3;
+    const bool vec_ok = (w % 4) == 0;
+    for (int i = tid; i < 2 * TH * QUADS; i += NT) {
+        const int q = i % QUADS, rest = i / QUADS;
+        const int r = rest % TH, lane = rest / TH;
+        const int gy = ty0 + r;
+        if (gy >= h || (lane == 1 && !has_b) || 4 * q >= valid_floats) continue;
+        const float4 v = *reinterpret_cast<const float4 *>(stage + (size_t)(lane * TH + r) * PITCH + 4 * q);
+        float *dst = out + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3 + 4 * q;
+        if (vec_ok && 4 * q + 4 <= valid_floats) {
+            *reinterpret_cast<float4 *>(dst) = v;
+        } else {
+            const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < valid_floats) dst[e] = vals[e];
+        }
+    }
+}
+
 __device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[kPX])
 {
     float4 *p = reinterpret_cast<float4 *>(dst);
@@ -352,7 +399,12 @@ struct TileB {
     static constexpr int CD_PITCH = round_pitch(kPX * D_RUNS > kPX * (E_RUNS - 1) + 10 ? kPX * D_RUNS
                                                                                        : kPX * (E_RUNS - 1) + 10);  // -1
     static constexpr int B_PLANE = B_ROWS * B_PITCH, CS_PLANE = CS_ROWS * CS_PITCH, CD_PLANE = CD_ROWS * CD_PITCH;
-    static constexpr size_t kSmemBytes = (size_t)(B_PLANE + CS_PLANE + 3 * CD_PLANE) * sizeof(f2) + 64;
+    // output staging (NHWC rows of one tile for both images), overlaid on sB + sCs once S4 is done. The row pitch is
+    // an odd multiple of 16 B: the run-per-lane 128-bit stores AND the linear copy-out loads are conflict-free.
+    static constexpr int ST_PITCH = TW * 3 + 4;                       // floats per staged row
+    static constexpr int STAGE_F2 = 2 * TH * ST_PITCH / 2;            // float2 slots
+    static constexpr int FRONT_F2 = B_PLANE + CS_PLANE > STAGE_F2 ? B_PLANE + CS_PLANE : STAGE_F2;
+    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE) * sizeof(f2) + 64;
     static_assert(TW % kPX == 0, "tile width must be a multiple of the run length");
 };
 
@@ -367,13 +419,18 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
     __shared__ __align__(8) uint64_t tma_bar;
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
-    f2 *sCD = sCs + T::CS_PLANE;                 // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
+    f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
+    float *sStage = reinterpret_cast<float *>(sB);   // [2][TH][ST_PITCH] NHWC staging, valid after the S4 barrier
     int *sWin = reinterpret_cast<int *>(sCD + 3 * T::CD_PLANE);   // [2 images][4 windows]
 
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
     const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
-    const int h = P.h, w = P.w;
+    int h = P.h, w = P.w, border = P.border;
+    float clip_max = P.clip_max;
+    // pin the epilogue's parameters in registers now: re-reading them from the constant bank after the long S5 loop
+    // showed up as ~10 % long-scoreboard stalls
+    asm volatile("" : "+r"(h), "+r"(w), "+r"(border), "+f"(clip_max), "+l"(orient), "+l"(line_end), "+l"(gray));
     int img0, img1;
     bool has_b;
     pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
@@ -523,34 +580,6 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
     }
     __syncthreads();
 
-    // ---- orient output: central TH x TW of d, coalesced 128-bit NHWC stores (4 consecutive floats = (pixel, channel))
-    if (orient) {
-        const float *sCDf = reinterpret_cast<const float *>(sCD);
-        const bool vec_ok = (w % 4) == 0;
-        constexpr int QUADS = TW * 3 / 4;
-        for (int i = tid; i < 2 * TH * QUADS; i += NT) {
-            const int q = i % QUADS, rest = i / QUADS;
-            const int r = rest % TH, lane = rest / TH;
-            const int gy = ty0 + r;
-            if (gy >= h || (lane == 1 && !has_b)) continue;
-            float vals[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int f = 4 * q + e, px = f / 3, ch = f - 3 * px;
-                vals[e] = sCDf[2 * (ch * T::CD_PLANE + (r + 1) * T::CD_PITCH + px + 1) + lane];
-            }
-            float *dst = orient + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3 + 4 * q;
-            const int last_px = tx0 + (4 * q + 3) / 3;
-            if (vec_ok && last_px < w) {
-                *reinterpret_cast<float4 *>(dst) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (tx0 + (4 * q + e) / 3 < w) dst[e] = vals[e];
-            }
-        }
-    }
-
     // ---- S5-S7: e = clip(relu(conv3x3(d, end))); p = mask * e; g = mean(p)                 recognition_testing.py:73-77
     for (int t = tid; t < TH * T::E_RUNS; t += NT) {
         const int r = t % TH, k = t / TH;
@@ -574,21 +603,20 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
                             acc[p][co] = fma2(P.w5[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
             }
         }
-        const bool row_in = gy >= P.border && gy < h - P.border;
-        const bool all_keep = row_in && gx0 >= P.border && gx0 + kPX <= w - P.border;   // run clear of the border mask
+        const bool row_in = gy >= border && gy < h - border;
+        const bool all_keep = row_in && gx0 >= border && gx0 + kPX <= w - border;   // run clear of the border mask
         const float third = __fdiv_rn(1.0f, 3.0f);
         f2 g[kPX];
 #pragma unroll
         for (int p = 0; p < kPX; ++p)
 #pragma unroll
             for (int co = 0; co < 3; ++co)
-                acc[p][co] = make_float2(clip_nan(relu_nan(acc[p][co].x), P.clip_max),
-                                         clip_nan(relu_nan(acc[p][co].y), P.clip_max));
+                acc[p][co] = make_float2(clip_nan(relu_nan(acc[p][co].x), clip_max), clip_nan(relu_nan(acc[p][co].y), clip_max));
         if (!all_keep) {
 #pragma unroll
             for (int p = 0; p < kPX; ++p) {
                 const int gx = gx0 + p;
-                if (row_in && gx >= P.border && gx < w - P.border) continue;
+                if (row_in && gx >= border && gx < w - border) continue;
 #pragma unroll
                 for (int co = 0; co < 3; ++co) {   // pad_inwards multiplies by 0: NaN stays NaN
                     const float a = acc[p][co].x, b = acc[p][co].y;
@@ -601,28 +629,14 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
             g[p] = mul2(add2(add2(acc[p][0], acc[p][1]), acc[p][2]), make_float2(third, third));
         const bool full = gx0 + kPX <= w;
         const bool vec_ok = full && (w % 4) == 0;
+        const size_t pix_a = ((size_t)img0 * h + gy) * w + gx0, pix_b = ((size_t)img1 * h + gy) * w + gx0;
+        // stage padded_line_end in NHWC order: 96 contiguous bytes per image and run; written out coalesced below
+        store_nhwc8<0>(sStage + (size_t)r * T::ST_PITCH + 3 * kPX * k, acc, true, kPX);
+        store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, acc, true, kPX);
 #pragma unroll
         for (int lane = 0; lane < 2; ++lane) {
             if (lane == 1 && !has_b) break;
-            const size_t pix = ((size_t)(lane ? img1 : img0) * h + gy) * w + gx0;
-            float vals[kPX * 3];
-#pragma unroll
-            for (int p = 0; p < kPX; ++p)
-#pragma unroll
-                for (int co = 0; co < 3; ++co) vals[3 * p + co] = lane ? acc[p][co].y : acc[p][co].x;
-            if (line_end) {
-                float *dst = line_end + pix * 3;
-                if (vec_ok) {
-#pragma unroll
-                    for (int q = 0; q < kPX * 3 / 4; ++q)
-                        reinterpret_cast<float4 *>(dst)[q] =
-                            make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < kPX * 3; ++e)
-                        if (gx0 + e / 3 < w) dst[e] = vals[e];
-                }
-            }
+            const size_t pix = lane ? pix_b : pix_a;
             if (gray) {
                 float *dst = gray + pix;
                 if (vec_ok) {
@@ -659,6 +673,28 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
                 }
             }
         }
+    }
+    // ---- coalesced copy-out: staged rows -> global NHWC (consecutive lanes write consecutive 16 bytes) -----------------
+    __syncthreads();
+    copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
+    if (orient) {
+        __syncthreads();
+        // orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5)
+        for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+            const int r = t % TH, k = t / TH;
+            f2 d[kPX][3];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                f2 v[10];
+                load_cols<5>(sCD + ci * T::CD_PLANE + (r + 1) * T::CD_PITCH + kPX * k, v);
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) d[p][ci] = v[p + 1];
+            }
+            store_nhwc8<0>(sStage + (size_t)r * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
+            store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
+        }
+        __syncthreads();
+        copy_out_tile<TH, TW, NT>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
     }
     if (P.win.count) {
         __syncthreads();
@@ -749,7 +785,7 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
     return SILENT_OK;
 }
 
-constexpr int kTileHA = 16, kTileHB = 32, kTileW = 64, kThreadsA = 128, kThreadsB = 256;
+constexpr int kTileHA = 16, kTileHB = 32, kTileW = 64, kThreadsA = 192, kThreadsB = 256;
 
 template <bool DW, bool RGBY, bool PAIRED>
 static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, dim3 grid, cudaStream_t stream)
