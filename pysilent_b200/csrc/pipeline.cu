@@ -57,6 +57,7 @@ silent_plan::~silent_plan()
         if (e) cudaEventDestroy(e);
     release(ws);
     if (d_tables) cudaFree(d_tables);
+    if (d_pair_words) cudaFree(d_pair_words);
 }
 
 extern "C" {

@@ -165,7 +165,7 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
 
     // geometry of the frame-pair pyramid kernel: per level and x tile, the span of frame-row words its x-taps touch
     plan->pair.assign(L, PairLevel());
-    plan->pair_ok = L > 0 && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3;
+    plan->pair_ok = L > 0 && L <= kPairMaxLevels && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3;
     for (int s = 0; s < L && plan->pair_ok; ++s) {
         PairLevel &pl = plan->pair[s];
         pl.ntx = ceil_div(w, kPairTileW);
@@ -225,6 +225,21 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
             if (e != cudaSuccess) {
                 delete plan;
                 return fail(SILENT_E_CUDA, "upload of tap tables failed: %s", cudaGetErrorString(e));
+            }
+            if (plan->pair_ok) {   // per-level / per-tile word spans of the frame-pair pyramid kernel
+                std::vector<int> words((size_t)L * kPairMaxTiles * 2, 0);
+                for (int s = 0; s < L; ++s)
+                    for (int t = 0; t < plan->pair[s].ntx; ++t) {
+                        words[((size_t)s * kPairMaxTiles + t) * 2] = plan->pair[s].word_lo[t];
+                        words[((size_t)s * kPairMaxTiles + t) * 2 + 1] = plan->pair[s].nwords[t];
+                    }
+                e = cudaMalloc(&plan->d_pair_words, words.size() * sizeof(int));
+                if (e == cudaSuccess)
+                    e = cudaMemcpy(plan->d_pair_words, words.data(), words.size() * sizeof(int), cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) {
+                    delete plan;
+                    return fail(SILENT_E_CUDA, "upload of pyramid tile spans failed: %s", cudaGetErrorString(e));
+                }
             }
             plan->on_device = true;
         }

@@ -14,6 +14,8 @@
 //                        shared memory; phase H gathers 6 of them per output sample. ~10x fewer instructions than the
 //                        per-pixel kernel (which re-converts every tap for every pixel). Output is the pair-interleaved
 //                        planar layout xpair[pair][c][y][x] = (frame A, frame B) that stack_a_kernel loads verbatim.
+#include <algorithm>
+
 #include "plan.h"
 #include "stack.h"
 
@@ -128,13 +130,16 @@ constexpr int kVGroup = 18;   // float2 slots per group of 16 byte-columns in th
 struct PairParams {
     const uint8_t *frames;
     f2 *xpair;
-    const int32_t *idx_y, *idx_x;   // tables of THIS level: [h][6], [w][6]
+    const int32_t *idx_y, *idx_x;   // tap tables of all levels: [L][h][6], [L][w][6]
     const float *w_y, *w_x;
+    const int *words;               // [L][kPairMaxTiles][2]: first 32-bit word of a frame row and word count per x tile
     int H, row_bytes, FC;           // frame rows, bytes per frame row, interleaved channels
-    int h, w, L, level, B;
-    int th;                         // output rows per tile
-    int vpitch;                     // float2 per row of the column-sum buffer
-    int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];   // per x tile: first 32-bit word of a frame row, word count
+    int h, w, L, B, ntx;
+    // ONE launch covers every level: blockIdx.x enumerates the tiles of a frame pair with the COARSEST level first (it
+    // pulls the whole frame through L2; the finer levels, whose crops are subsets, then hit L2), blockIdx.y the pair.
+    int th[kPairMaxLevels];           // output rows per tile
+    int vpitch[kPairMaxLevels];       // float2 per row of the column-sum buffer
+    int tile_start[kPairMaxLevels + 1];   // by order position k (level = L - 1 - k)
 };
 
 // byte k of `word` as an exact float: PRMT builds the bit pattern of 2^23 + byte, the caller subtracts 2^23 (FADD2)
@@ -143,32 +148,38 @@ __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t selector)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, selector));
 }
 
-__global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid_constant__ PairParams P)
+__global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __grid_constant__ PairParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     f2 *sV = reinterpret_cast<f2 *>(smem_raw);                          // [th][vpitch] column sums (frame A, frame B)
-    int *sTy = reinterpret_cast<int *>(sV + (size_t)P.th * P.vpitch);   // [th][6] source rows (-1: row is zero)
-    float *sWy = reinterpret_cast<float *>(sTy + P.th * kTaps);         // [th][6]
 
     const int tid = threadIdx.x;
-    const int bx = blockIdx.x, by = blockIdx.y, q = blockIdx.z;
-    const int th = P.th, h = P.h, w = P.w;
+    int k = 0;
+    while (k + 1 < P.L && (int)blockIdx.x >= P.tile_start[k + 1]) ++k;
+    const int level = P.L - 1 - k, local = blockIdx.x - P.tile_start[k];
+    const int bx = local % P.ntx, by = local / P.ntx, q = blockIdx.y;
+    const int th = P.th[level], vpitch = P.vpitch[level], h = P.h, w = P.w;
+    const int32_t *idx_y = P.idx_y + (size_t)level * h * kTaps, *idx_x = P.idx_x + (size_t)level * w * kTaps;
+    const float *w_y = P.w_y + (size_t)level * h * kTaps, *w_x = P.w_x + (size_t)level * w * kTaps;
     const int oy0 = by * th;
+    int *sTy = reinterpret_cast<int *>(sV + (size_t)th * vpitch);   // [th][6] source rows (-1: row is zero)
+    float *sWy = reinterpret_cast<float *>(sTy + th * kTaps);       // [th][6]
     const size_t frame_bytes = (size_t)P.H * P.row_bytes;
     const uint8_t *frameA = P.frames + (size_t)(2 * q) * frame_bytes;
     const uint8_t *frameB = (2 * q + 1 < P.B) ? frameA + frame_bytes : frameA;
 
     for (int i = tid; i < th * kTaps; i += kPairThreads) {
         const int oy = oy0 + i / kTaps;
-        const bool ok = oy < h && __ldg(P.idx_y + (size_t)oy * kTaps) >= 0;
-        sTy[i] = ok ? __ldg(P.idx_y + (size_t)oy * kTaps + i % kTaps) : -1;
-        sWy[i] = ok ? __ldg(P.w_y + (size_t)oy * kTaps + i % kTaps) : 0.0f;
+        const bool ok = oy < h && __ldg(idx_y + (size_t)oy * kTaps) >= 0;
+        sTy[i] = ok ? __ldg(idx_y + (size_t)oy * kTaps + i % kTaps) : -1;
+        sWy[i] = ok ? __ldg(w_y + (size_t)oy * kTaps + i % kTaps) : 0.0f;
     }
     __syncthreads();
 
     // ---- phase V: column sums over the 6 y-taps, 16 byte-columns (one aligned 128-bit load per tap row and frame) per
     //      task: 12 independent 16-byte loads in flight per thread cover the HBM/L2 latency ---------------------------
-    const int nw = P.nwords[bx], wlo = P.word_lo[bx];   // multiples of 4 words
+    const int wlo = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2);   // multiples of 4 words
+    const int nw = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2 + 1);
     const int nq = nw >> 2;
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
     for (int t = tid; t < th * nq; t += kPairThreads) {
@@ -199,44 +210,38 @@ __global__ void __launch_bounds__(kPairThreads) pyramid_pair_kernel(const __grid
             }
         }
         // 16 columns = 128 B per task: padded to 144 B so consecutive lanes start in consecutive 16-byte bank groups
-        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * P.vpitch + kVGroup * qi);
+        float4 *dst = reinterpret_cast<float4 *>(sV + (size_t)r * vpitch + kVGroup * qi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) dst[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
     }
     __syncthreads();
 
-    // ---- phase H: chain over the 6 x-taps; a thread owns one output column and walks every 4th row of the tile --------
-    constexpr int ROW_GROUPS = kPairThreads / kPairTileW;
+    // ---- phase H: chain over the 6 x-taps. A thread owns one (output column, channel) and walks all rows of the tile:
+    //      its six column-sum offsets and weights are set up once, each row then costs 6 LDS.64 + 6 FFMA2 + 1 store.
+    //      (192 of the 256 threads work here; consecutive lanes = consecutive columns, so the stores are coalesced.)
+    const int c = tid / kPairTileW;
     const int ox = bx * kPairTileW + (tid % kPairTileW);
-    if (ox >= w) return;
-    const int32_t *tx = P.idx_x + (size_t)ox * kTaps;
+    if (c >= 3 || ox >= w) return;
+    const int32_t *tx = idx_x + (size_t)ox * kTaps;
     const bool col_ok = __ldg(tx) >= 0;
-    int bc[kTaps];
+    int off[kTaps];
     f2 wx[kTaps];
 #pragma unroll
     for (int i = 0; i < kTaps; ++i) {
-        bc[i] = col_ok ? __ldg(tx + i) * P.FC - 4 * wlo : 0;
-        const float v = col_ok ? __ldg(P.w_x + (size_t)ox * kTaps + i) : 0.0f;
+        const int b = col_ok ? __ldg(tx + i) * P.FC - 4 * wlo + c : 0;
+        off[i] = b + (kVGroup - 16) * (b >> 4);   // position in the padded column-sum row
+        const float v = col_ok ? __ldg(w_x + (size_t)ox * kTaps + i) : 0.0f;
         wx[i] = make_float2(v, v);
     }
     const size_t plane = (size_t)h * w;
-    f2 *out = P.xpair + ((size_t)q * P.L + P.level) * 3 * plane + ox;
-    for (int r = tid / kPairTileW; r < th; r += ROW_GROUPS) {
-        const int oy = oy0 + r;
-        if (oy >= h) break;
-        const f2 *row = sV + (size_t)r * P.vpitch;
+    f2 *out = P.xpair + (((size_t)q * P.L + level) * 3 + c) * plane + (size_t)oy0 * w + ox;
+    const int rows = min(th, h - oy0);
+    for (int r = 0; r < rows; ++r) {
+        const f2 *row = sV + (size_t)r * vpitch;
+        f2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            f2 acc = make_float2(0.0f, 0.0f);
-            if (col_ok) {
-#pragma unroll
-                for (int i = 0; i < kTaps; ++i) {
-                    const int b = bc[i] + c;
-                    acc = __ffma2_rn(wx[i], row[b + (kVGroup - 16) * (b >> 4)], acc);
-                }
-            }
-            out[c * plane + (size_t)oy * w] = acc;
-        }
+        for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[off[i]], acc);   // zero weights when !col_ok
+        out[(size_t)r * w] = acc;
     }
 }
 
@@ -265,27 +270,30 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
         SILENT_CUDA(cudaFuncSetAttribute(pyramid_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    for (int s = 0; s < plan->levels; ++s) {
+    PairParams P;
+    P.frames = (const uint8_t *)frames_dev;
+    P.xpair = (f2 *)xpair_dev;
+    P.idx_y = plan->d_idx_y, P.w_y = plan->d_w_y, P.idx_x = plan->d_idx_x, P.w_x = plan->d_w_x;
+    P.words = plan->d_pair_words;
+    P.H = p.frame_h;
+    P.row_bytes = p.frame_w * p.frame_c;
+    P.FC = p.frame_c;
+    P.h = plan->h, P.w = plan->w, P.L = plan->levels, P.B = batch;
+    P.ntx = plan->pair[0].ntx;
+    size_t smem = 0;
+    int tiles = 0;
+    for (int k = 0; k < plan->levels; ++k) {   // coarsest level first
+        const int s = plan->levels - 1 - k;
         const PairLevel &pl = plan->pair[s];
-        PairParams P;
-        P.frames = (const uint8_t *)frames_dev;
-        P.xpair = (f2 *)xpair_dev;
-        P.idx_y = plan->d_idx_y + (size_t)s * plan->h * kTaps;
-        P.w_y = plan->d_w_y + (size_t)s * plan->h * kTaps;
-        P.idx_x = plan->d_idx_x + (size_t)s * plan->w * kTaps;
-        P.w_x = plan->d_w_x + (size_t)s * plan->w * kTaps;
-        P.H = p.frame_h;
-        P.row_bytes = p.frame_w * p.frame_c;
-        P.FC = p.frame_c;
-        P.h = plan->h, P.w = plan->w, P.L = plan->levels, P.level = s, P.B = batch;
-        P.th = pl.th;
-        P.vpitch = pl.vpitch;
-        for (int t = 0; t < pl.ntx; ++t) P.word_lo[t] = pl.word_lo[t], P.nwords[t] = pl.nwords[t];
-        const size_t smem = (size_t)pl.th * pl.vpitch * sizeof(f2) + (size_t)pl.th * kTaps * 8;
-        dim3 grid(pl.ntx, ceil_div(plan->h, pl.th), pairs);
-        pyramid_pair_kernel<<<grid, kPairThreads, smem, stream>>>(P);
-        SILENT_LAUNCH_CHECK("pyramid_pair_kernel");
+        P.th[s] = pl.th;
+        P.vpitch[s] = pl.vpitch;
+        P.tile_start[k] = tiles;
+        tiles += pl.ntx * ceil_div(plan->h, pl.th);
+        smem = std::max(smem, (size_t)pl.th * pl.vpitch * sizeof(f2) + (size_t)pl.th * kTaps * 8);
     }
+    P.tile_start[plan->levels] = tiles;
+    pyramid_pair_kernel<<<dim3(tiles, pairs), kPairThreads, smem, stream>>>(P);
+    SILENT_LAUNCH_CHECK("pyramid_pair_kernel");
     return SILENT_OK;
 }
 
