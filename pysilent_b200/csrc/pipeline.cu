@@ -26,6 +26,12 @@ static void release(Workspace &ws)
     cudaFreeHost(ws.h_line_end);
     cudaFreeHost(ws.h_points);
     cudaFreeHost(ws.h_count);
+    for (cudaEvent_t e : ws.ev_in)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ws.ev_done)
+        if (e) cudaEventDestroy(e);
+    if (ws.s_in) cudaStreamDestroy(ws.s_in);
+    if (ws.s_out) cudaStreamDestroy(ws.s_out);
     ws = Workspace();
 }
 
@@ -96,44 +102,70 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     return SILENT_OK;
 }
 
-int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
-                        float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
-                        int64_t capacity, int64_t *count_dev, silent_stream stream)
+// K1 + K2 for frames [frame0, frame0 + nb) of a batch: the outputs, gray and the region maxima of these frames land at
+// their place in the whole-batch tensors, so that the emit stage can run once over the batch afterwards. frame0 must be
+// even on the frame-pair path (pairs never straddle a chunk).
+static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, const void *frames_dev, int frame0, int nb,
+                            float *pyramid_dev, float *orient_dev, float *line_end_dev, const WindowGeom *geo,
+                            cudaStream_t s)
 {
-    if (!plan || !weights_host || !frames_dev) return fail(SILENT_E_INVAL, "silent_pipeline_run: null argument");
+    Workspace &ws = plan->ws;
+    const bool pair_path = pyramid_pair_supported(plan);
+    const size_t level_elems = (size_t)plan->h * plan->w;
+    const size_t img0 = (size_t)frame0 * plan->levels;
+    const int n = nb * plan->levels;
+    const unsigned char *frames = (const unsigned char *)frames_dev + frame_bytes(plan) * frame0;
+    int rc = SILENT_OK;
+    // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
+    // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
+    if (pyramid_dev || !pair_path) {
+        float *dst = pyramid_dev ? pyramid_dev + img0 * level_elems * plan->params.num_colors : ws.d_pyramid;
+        rc = pyramid_build(plan, frames, nb, dst, s);
+        if (rc != SILENT_OK) return rc;
+    }
+    if (pair_path) {
+        rc = pyramid_pair_build(plan, frames, nb, ws.d_pyramid, s);
+        if (rc != SILENT_OK) return rc;
+    }
+    const void *pyr = pair_path ? (const void *)ws.d_pyramid
+                                : (const void *)(pyramid_dev ? pyramid_dev + img0 * level_elems * 3 : ws.d_pyramid);
+    if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
+    return stack_fused(pyr, n, plan->h, plan->w, pair_path ? plan->levels : 0, W,
+                       orient_dev ? orient_dev + img0 * level_elems * 3 : nullptr,
+                       line_end_dev ? line_end_dev + img0 * level_elems * 3 : nullptr, ws.d_gray + img0 * level_elems,
+                       ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr, s);
+}
+
+static int check_pipeline_args(const silent_plan *plan, const silent_stack_weights *W, const void *frames, int batch)
+{
+    if (!plan || !W || !frames) return fail(SILENT_E_INVAL, "silent_pipeline_run: null argument");
     if (batch <= 0) return fail(SILENT_E_INVAL, "batch must be positive");
     if (plan->params.num_colors != 3) return fail(SILENT_E_SHAPE, "the fused stack needs num_colors == 3");
     if (plan->levels == 0) return fail(SILENT_E_SHAPE, "frame is not larger than the pyramid centre: 0 levels");
     if ((plan->h % 2) || (plan->w % 2))
         return fail(SILENT_E_SHAPE, "Ambiguous dimension: region shape (h/2, w/2) must be integral (h=%d, w=%d)", plan->h,
                     plan->w);
+    return SILENT_OK;
+}
+
+int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
+                        float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
+                        int64_t capacity, int64_t *count_dev, silent_stream stream)
+{
+    int rc = check_pipeline_args(plan, weights_host, frames_dev, batch);
+    if (rc != SILENT_OK) return rc;
     Workspace &ws = plan->ws;
     if (ws.batch < batch)
         return fail(SILENT_E_CAPACITY, "plan workspace holds %d frames, need %d: call silent_plan_reserve", ws.batch, batch);
     cudaStream_t s = (cudaStream_t)stream;
     const int n = batch * plan->levels;
-    // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
-    // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
-    const bool pair_path = pyramid_pair_supported(plan);
     const bool timing = plan->timing;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[0], s));
-    int rc = SILENT_OK;
-    if (pyramid_dev || !pair_path) {
-        rc = pyramid_build(plan, frames_dev, batch, pyramid_dev ? pyramid_dev : ws.d_pyramid, s);
-        if (rc != SILENT_OK) return rc;
-    }
-    if (pair_path) {
-        rc = pyramid_pair_build(plan, frames_dev, batch, ws.d_pyramid, s);
-        if (rc != SILENT_OK) return rc;
-    }
-    const void *pyr = pair_path ? (const void *)ws.d_pyramid : (const void *)(pyramid_dev ? pyramid_dev : ws.d_pyramid);
-    if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
     WindowGeom geo;
     const bool fuse_windows = count_dev && window_geometry(plan->h, plan->w, plan->h / 2, plan->w / 2, &geo);
     if (fuse_windows) SILENT_CUDA(cudaMemsetAsync(ws.d_winmax, 0, (size_t)n * geo.count * sizeof(int), s));
-    rc = stack_fused(pyr, n, plan->h, plan->w, pair_path ? plan->levels : 0, weights_host, orient_dev, line_end_dev,
-                     ws.d_gray, ws.d_stack, ws.stack_bytes, fuse_windows ? &geo : nullptr,
-                     fuse_windows ? ws.d_winmax : nullptr, s);
+    rc = run_stack_stages(plan, weights_host, frames_dev, 0, batch, pyramid_dev, orient_dev, line_end_dev,
+                          fuse_windows ? &geo : nullptr, s);
     if (rc != SILENT_OK) return rc;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
     if (count_dev)
@@ -164,48 +196,100 @@ int silent_plan_stage_ms(silent_plan *plan, float *pyramid_ms, float *stack_ms, 
     return SILENT_OK;
 }
 
+// Frames per chunk of the host-buffer pipeline: even (frame pairs), at most kMaxChunks chunks per call.
+static int host_chunk_frames(int batch)
+{
+    int per = (batch + 7) / 8;
+    per = std::max(per, 2);
+    per += per & 1;
+    while ((batch + per - 1) / per > kMaxChunks) per += 2;
+    return per;
+}
+
 int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_host,
                              int batch, float *orient_host, float *line_end_host, int64_t *points_host,
                              int64_t capacity, int64_t *count_host, silent_stream stream)
 {
-    if (!plan || !weights_host || !frames_host) return fail(SILENT_E_INVAL, "silent_pipeline_run_host: null argument");
-    if (batch <= 0) return fail(SILENT_E_INVAL, "batch must be positive");
+    int rc = check_pipeline_args(plan, weights_host, frames_host, batch);
+    if (rc != SILENT_OK) return rc;
     if (capacity < 0) return fail(SILENT_E_INVAL, "capacity must be >= 0");
-    int rc = silent_plan_reserve(plan, batch);
+    rc = silent_plan_reserve(plan, batch);
     if (rc != SILENT_OK) return rc;
     Workspace &ws = plan->ws;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t in_bytes = frame_bytes(plan) * batch;
+    const size_t fbytes = frame_bytes(plan);
     const size_t n = (size_t)batch * plan->levels;
-    const size_t tensor_bytes = n * plan->h * plan->w * 3 * sizeof(float);
+    const size_t image_bytes = (size_t)plan->h * plan->w * 3 * sizeof(float);
+    const size_t cap_tensor_bytes = (size_t)ws.batch * plan->levels * image_bytes;
 
-    const void *src = frames_host;
-    const size_t cap_tensor_bytes = (size_t)ws.batch * plan->levels * plan->h * plan->w * 3 * sizeof(float);
-    if (!is_pinned(frames_host)) {
-        if (!ws.h_frames) SILENT_CUDA(cudaMallocHost(&ws.h_frames, frame_bytes(plan) * ws.batch));
-        std::memcpy(ws.h_frames, frames_host, in_bytes);
-        src = ws.h_frames;
+    // Three queues: s_in (host -> HBM), the caller's stream (kernels), s_out (HBM -> host). The batch is cut into chunks
+    // of whole frame pairs; chunk c + 1 uploads while chunk c computes and chunk c - 1 downloads, so on a full-duplex
+    // PCIe link the call costs about max(upload, download) instead of their sum.
+    if (!ws.s_in) SILENT_CUDA(cudaStreamCreateWithFlags(&ws.s_in, cudaStreamNonBlocking));
+    if (!ws.s_out) SILENT_CUDA(cudaStreamCreateWithFlags(&ws.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < kMaxChunks; ++i) {
+        if (!ws.ev_in[i]) SILENT_CUDA(cudaEventCreateWithFlags(&ws.ev_in[i], cudaEventDisableTiming));
+        if (!ws.ev_done[i]) SILENT_CUDA(cudaEventCreateWithFlags(&ws.ev_done[i], cudaEventDisableTiming));
     }
-    SILENT_CUDA(cudaMemcpyAsync(ws.d_frames, src, in_bytes, cudaMemcpyHostToDevice, s));
-    const int64_t cap = capacity < ws.points_capacity ? capacity : ws.points_capacity;
-    rc = silent_pipeline_run(plan, weights_host, ws.d_frames, batch, nullptr, orient_host ? ws.d_orient : nullptr,
-                             line_end_host ? ws.d_line_end : nullptr, ws.d_points, cap, ws.d_count, stream);
-    if (rc != SILENT_OK) return rc;
+    const bool frames_direct = is_pinned(frames_host);
     const bool orient_direct = orient_host && is_pinned(orient_host);
     const bool line_end_direct = line_end_host && is_pinned(line_end_host);
+    if (!frames_direct && !ws.h_frames) SILENT_CUDA(cudaMallocHost(&ws.h_frames, fbytes * ws.batch));
     if (orient_host && !orient_direct && !ws.h_orient) SILENT_CUDA(cudaMallocHost(&ws.h_orient, cap_tensor_bytes));
     if (line_end_host && !line_end_direct && !ws.h_line_end)
         SILENT_CUDA(cudaMallocHost(&ws.h_line_end, cap_tensor_bytes));
-    if (orient_host)
-        SILENT_CUDA(cudaMemcpyAsync(orient_direct ? orient_host : ws.h_orient, ws.d_orient, tensor_bytes,
-                                    cudaMemcpyDeviceToHost, s));
-    if (line_end_host)
-        SILENT_CUDA(cudaMemcpyAsync(line_end_direct ? line_end_host : ws.h_line_end, ws.d_line_end, tensor_bytes,
-                                    cudaMemcpyDeviceToHost, s));
-    SILENT_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    if (points_host && cap > 0)
-        SILENT_CUDA(cudaMemcpyAsync(ws.h_points, ws.d_points, cap * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    char *orient_dst = (char *)(orient_direct ? orient_host : ws.h_orient);
+    char *line_end_dst = (char *)(line_end_direct ? line_end_host : ws.h_line_end);
+
+    WindowGeom geo;
+    const bool fuse_windows = window_geometry(plan->h, plan->w, plan->h / 2, plan->w / 2, &geo);
+    // work queued on the caller's stream before this call stays ordered before anything we overwrite
+    SILENT_CUDA(cudaEventRecord(ws.ev_done[0], s));
+    SILENT_CUDA(cudaStreamWaitEvent(ws.s_in, ws.ev_done[0], 0));
+    SILENT_CUDA(cudaStreamWaitEvent(ws.s_out, ws.ev_done[0], 0));
+    if (fuse_windows) SILENT_CUDA(cudaMemsetAsync(ws.d_winmax, 0, n * geo.count * sizeof(int), s));
+    const int per = host_chunk_frames(batch);
+    int chunk = 0;
+    for (int f0 = 0; f0 < batch; f0 += per, ++chunk) {
+        const int nb = std::min(per, batch - f0);
+        const char *src = (const char *)frames_host + fbytes * f0;
+        if (!frames_direct) {
+            std::memcpy((char *)ws.h_frames + fbytes * f0, src, fbytes * nb);
+            src = (const char *)ws.h_frames + fbytes * f0;
+        }
+        SILENT_CUDA(cudaMemcpyAsync((char *)ws.d_frames + fbytes * f0, src, fbytes * nb, cudaMemcpyHostToDevice, ws.s_in));
+        SILENT_CUDA(cudaEventRecord(ws.ev_in[chunk], ws.s_in));
+        SILENT_CUDA(cudaStreamWaitEvent(s, ws.ev_in[chunk], 0));
+        rc = run_stack_stages(plan, weights_host, ws.d_frames, f0, nb, nullptr, orient_host ? ws.d_orient : nullptr,
+                              line_end_host ? ws.d_line_end : nullptr, fuse_windows ? &geo : nullptr, s);
+        if (rc != SILENT_OK) break;
+        SILENT_CUDA(cudaEventRecord(ws.ev_done[chunk], s));
+        SILENT_CUDA(cudaStreamWaitEvent(ws.s_out, ws.ev_done[chunk], 0));
+        const size_t off = (size_t)f0 * plan->levels * image_bytes, bytes = (size_t)nb * plan->levels * image_bytes;
+        if (orient_host)
+            SILENT_CUDA(cudaMemcpyAsync(orient_dst + off, (char *)ws.d_orient + off, bytes, cudaMemcpyDeviceToHost, ws.s_out));
+        if (line_end_host)
+            SILENT_CUDA(cudaMemcpyAsync(line_end_dst + off, (char *)ws.d_line_end + off, bytes, cudaMemcpyDeviceToHost,
+                                        ws.s_out));
+    }
+    if (rc != SILENT_OK) {   // drain what was queued before reporting the failure
+        cudaStreamSynchronize(ws.s_in);
+        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(ws.s_out);
+        return rc;
+    }
+    const int64_t cap = capacity < ws.points_capacity ? capacity : ws.points_capacity;
+    rc = max_value_indices_region(ws.d_gray, (int)n, plan->h, plan->w, plan->h / 2, plan->w / 2, ws.d_points, cap,
+                                  ws.d_count, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, s);
+    if (rc == SILENT_OK) {
+        SILENT_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (points_host && cap > 0)
+            SILENT_CUDA(cudaMemcpyAsync(ws.h_points, ws.d_points, cap * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    }
     SILENT_CUDA(cudaStreamSynchronize(s));
+    SILENT_CUDA(cudaStreamSynchronize(ws.s_out));
+    if (rc != SILENT_OK) return rc;
+    const size_t tensor_bytes = n * image_bytes;
     if (orient_host && !orient_direct) std::memcpy(orient_host, ws.h_orient, tensor_bytes);
     if (line_end_host && !line_end_direct) std::memcpy(line_end_host, ws.h_line_end, tensor_bytes);
     const int64_t total = *ws.h_count;

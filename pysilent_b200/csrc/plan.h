@@ -20,6 +20,8 @@ struct PairLevel {
     int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];
 };
 
+constexpr int kMaxChunks = 16;   // chunks per silent_pipeline_run_host call
+
 // Plan-owned device scratch, sized by silent_plan_reserve(max_batch).
 struct Workspace {
     int batch = 0;
@@ -41,6 +43,9 @@ struct Workspace {
     float *h_line_end = nullptr;
     int64_t *h_points = nullptr;
     int64_t *h_count = nullptr;
+    // silent_pipeline_run_host: upload / download queues and per-chunk events (chunked, overlapped transfers)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
 };
 
 }  // namespace silent

@@ -83,6 +83,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// ---- bulk stores (cp.async.bulk shared -> global): one instruction moves a whole staged row; the TMA unit does the
+//      address arithmetic that a per-float4 copy loop spent ~30 instructions on
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // smallest pitch (in float2) >= n whose byte stride is an odd multiple of 16: conflict-free 128-bit row-strided access
 constexpr int round_pitch(int n) { return n + ((2 - n % 4) + 4) % 4; }
 
@@ -142,6 +153,22 @@ __device__ __forceinline__ void copy_out_tile(const float *__restrict__ stage, f
             for (int e = 0; e < 4; ++e)
                 if (4 * q + e < valid_floats) dst[e] = vals[e];
         }
+    }
+}
+
+// Same tile through the TMA unit: thread t < 2 * TH issues ONE bulk store of its staged row (needs 16-byte aligned rows:
+// w % 4 == 0). The caller fences + barriers before, and waits (bulk_wait_read) before the staging buffer is reused.
+template <int TH, int TW>
+__device__ __forceinline__ void copy_out_rows_bulk(const float *__restrict__ stage, float *__restrict__ out, int img0,
+                                                   int img1, bool has_b, int ty0, int tx0, int h, int w, int tid)
+{
+    constexpr int PITCH = TW * 3 + 4;
+    if (tid < 2 * TH) {
+        const int lane = tid / TH, r = tid - lane * TH, gy = ty0 + r;
+        if (gy < h && (lane == 0 || has_b))
+            bulk_store(out + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3, stage + (size_t)tid * PITCH,
+                       (uint32_t)(min(TW, w - tx0) * 3 * sizeof(float)));
+        bulk_commit();
     }
 }
 
@@ -409,7 +436,7 @@ struct TileB {
 };
 
 template <int TH, int TW, int NT>
-__global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
+__global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
                                                      const __grid_constant__ CUtensorMap tmap, float *__restrict__ orient,
                                                      float *__restrict__ line_end, float *__restrict__ gray,
                                                      int *__restrict__ winmax)
@@ -505,13 +532,18 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
         store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
         const int rd = r - 3;   // row in the CD planes (origin -1)
         if (rd >= 0 && rd < T::CD_ROWS) {
+            // column -4 + 8k + p sits at idx = 8k - 3 + p of the CD planes (origin -1): odd p starts an aligned pair
+            const int base = kPX * k - 3;
 #pragma unroll
-            for (int p = 0; p < kPX; ++p) {
-                const int idx = kPX * k - 3 + p;   // column -4 + 8k + p relative to origin -1
-                if (idx >= 0 && idx < T::CD_PITCH) {
+            for (int co = 0; co < 3; ++co) {
+                f2 *row = sCD + co * T::CD_PLANE + rd * T::CD_PITCH;
+                if (base >= 0 && base < T::CD_PITCH) row[base] = acc[0][co];
 #pragma unroll
-                    for (int co = 0; co < 3; ++co) sCD[co * T::CD_PLANE + rd * T::CD_PITCH + idx] = acc[p][co];
-                }
+                for (int p = 1; p + 1 < kPX; p += 2)
+                    if (base + p >= 0 && base + p + 1 < T::CD_PITCH)
+                        *reinterpret_cast<float4 *>(row + base + p) =
+                            make_float4(acc[p][co].x, acc[p][co].y, acc[p + 1][co].x, acc[p + 1][co].y);
+                if (base + kPX - 1 < T::CD_PITCH) row[base + kPX - 1] = acc[kPX - 1][co];
             }
         }
     }
@@ -580,12 +612,39 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
     }
     __syncthreads();
 
+    // ---- orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5) and hand
+    //      the rows to the TMA unit; the copy drains while S5 computes -----------------------------------------------
+    const bool bulk_ok = (w % 4) == 0;   // staged rows start and end on 16-byte boundaries of the global tensors
+    if (orient) {
+        for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+            const int r = t % TH, k = t / TH;
+            f2 d[kPX][3];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                f2 v[10];
+                load_cols<5>(sCD + ci * T::CD_PLANE + (r + 1) * T::CD_PITCH + kPX * k, v);
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) d[p][ci] = v[p + 1];
+            }
+            store_nhwc8<0>(sStage + (size_t)r * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
+            store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (bulk_ok) {
+            copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
+        } else {
+            copy_out_tile<TH, TW, NT>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
+        }
+    }
+
     // ---- S5-S7: e = clip(relu(conv3x3(d, end))); p = mask * e; g = mean(p)                 recognition_testing.py:73-77
-    for (int t = tid; t < TH * T::E_RUNS; t += NT) {
-        const int r = t % TH, k = t / TH;
-        const int gy = ty0 + r, gx0 = tx0 + kPX * k;
-        if (gy >= h || gx0 >= w) continue;
-        f2 acc[kPX][3];
+    static_assert(NT >= TH * T::E_RUNS, "one S5 task per thread");
+    const int r5 = tid % TH, k5 = tid / TH;
+    const int gy = ty0 + r5, gx0 = tx0 + kPX * k5;
+    const bool active = tid < TH * T::E_RUNS && gy < h && gx0 < w;
+    f2 acc[kPX][3];
+    if (active) {
 #pragma unroll
         for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
 #pragma unroll
@@ -593,7 +652,7 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
                 f2 v[10];
-                load_cols<5>(sCD + ci * T::CD_PLANE + (r + ky) * T::CD_PITCH + kPX * k, v);
+                load_cols<5>(sCD + ci * T::CD_PLANE + (r5 + ky) * T::CD_PITCH + kPX * k5, v);
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -603,6 +662,13 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
                             acc[p][co] = fma2(P.w5[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
             }
         }
+    }
+    // the staging buffer is free again once the orient rows have been read out
+    if (orient) {
+        if (bulk_ok && tid < 2 * TH) bulk_wait_read();
+        __syncthreads();
+    }
+    if (active) {
         const bool row_in = gy >= border && gy < h - border;
         const bool all_keep = row_in && gx0 >= border && gx0 + kPX <= w - border;   // run clear of the border mask
         const float third = __fdiv_rn(1.0f, 3.0f);
@@ -630,9 +696,9 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
         const bool full = gx0 + kPX <= w;
         const bool vec_ok = full && (w % 4) == 0;
         const size_t pix_a = ((size_t)img0 * h + gy) * w + gx0, pix_b = ((size_t)img1 * h + gy) * w + gx0;
-        // stage padded_line_end in NHWC order: 96 contiguous bytes per image and run; written out coalesced below
-        store_nhwc8<0>(sStage + (size_t)r * T::ST_PITCH + 3 * kPX * k, acc, true, kPX);
-        store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, acc, true, kPX);
+        // stage padded_line_end in NHWC order: 96 contiguous bytes per image and run; written out row by row below
+        store_nhwc8<0>(sStage + (size_t)r5 * T::ST_PITCH + 3 * kPX * k5, acc, true, kPX);
+        store_nhwc8<1>(sStage + (size_t)(TH + r5) * T::ST_PITCH + 3 * kPX * k5, acc, true, kPX);
 #pragma unroll
         for (int lane = 0; lane < 2; ++lane) {
             if (lane == 1 && !has_b) break;
@@ -674,36 +740,24 @@ __global__ void __launch_bounds__(NT) stack_b_kernel(const f2 *__restrict__ bsum
             }
         }
     }
-    // ---- coalesced copy-out: staged rows -> global NHWC (consecutive lanes write consecutive 16 bytes) -----------------
+    // ---- copy-out: staged rows -> global NHWC, one bulk store per row ---------------------------------------------------
+    fence_async_smem();
     __syncthreads();
-    copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
-    if (orient) {
-        __syncthreads();
-        // orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5)
-        for (int t = tid; t < TH * T::E_RUNS; t += NT) {
-            const int r = t % TH, k = t / TH;
-            f2 d[kPX][3];
-#pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                f2 v[10];
-                load_cols<5>(sCD + ci * T::CD_PLANE + (r + 1) * T::CD_PITCH + kPX * k, v);
-#pragma unroll
-                for (int p = 0; p < kPX; ++p) d[p][ci] = v[p + 1];
-            }
-            store_nhwc8<0>(sStage + (size_t)r * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
-            store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
+    if (line_end) {
+        if (bulk_ok) {
+            copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
+        } else {
+            copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
         }
-        __syncthreads();
-        copy_out_tile<TH, TW, NT>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
     }
     if (P.win.count) {
-        __syncthreads();
         if (tid < 8) {
             const int lane = tid >> 2, win = tid & 3;
             if (win < P.win.count && (lane == 0 || has_b) && sWin[tid] != 0)
                 atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], sWin[tid]);
         }
     }
+    if (line_end && bulk_ok && tid < 2 * TH) bulk_wait_read();   // the CTA's shared memory must outlive the reads
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -785,14 +839,29 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
     return SILENT_OK;
 }
 
-constexpr int kTileHA = 16, kTileHB = 32, kTileW = 64, kThreadsA = 192, kThreadsB = 256;
+constexpr int kTileHA = 16, kTileHB = 32;
 
-template <bool DW, bool RGBY, bool PAIRED>
-static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, dim3 grid, cudaStream_t stream)
+// Tile width: the candidate that wastes the fewest columns of the last tile (288-wide levels: 6 x 48 instead of 4.5 x 64).
+static int pick_tile_w(int w) { return ceil_div(w, 48) * 48 < ceil_div(w, 64) * 64 ? 48 : 64; }
+// threads of stack_a: one warp-rounded round of S1 (its widest phase)
+template <int TW>
+struct ThreadsA {
+    static constexpr int value = (TileA<kTileHA, TW>::A_ROWS * TileA<kTileHA, TW>::A_RUNS + 31) / 32 * 32;
+};
+// threads of stack_b: one warp-rounded round of its widest phase (S3), which also covers one S5 task per thread
+template <int TW>
+struct ThreadsB {
+    static constexpr int value = ((kTileHB + 8) * TileB<kTileHB, TW>::C_RUNS + 31) / 32 * 32;
+};
+
+template <int TW, bool DW, bool RGBY, bool PAIRED>
+static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, int pairs, cudaStream_t stream)
 {
-    using T = TileA<kTileHA, kTileW>;
-    auto kern = stack_a_kernel<kTileHA, kTileW, kThreadsA, DW, RGBY, PAIRED>;
+    using T = TileA<kTileHA, TW>;
+    constexpr int kThreadsA = ThreadsA<TW>::value;
+    auto kern = stack_a_kernel<kTileHA, TW, kThreadsA, DW, RGBY, PAIRED>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
+    const dim3 grid(ceil_div(P.w, TW), ceil_div(P.h, kTileHA), pairs);
     kern<<<grid, kThreadsA, T::kSmemBytes, stream>>>(pyr, P, tmap, bsum2);
     SILENT_LAUNCH_CHECK("stack_a_kernel");
     return SILENT_OK;
@@ -801,19 +870,43 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
 // room for one float2 plane per image pair (n images pair up into at most (n + levels) / 2 pairs for any pairing)
 size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 256; }
 
-// winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
-template <bool PAIRED>
-static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, dim3 grid,
+template <int TW, bool PAIRED>
+static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, int pairs,
                       cudaStream_t stream)
 {
-    if (dw && rgby) return launch_a<true, true, PAIRED>(in, P, tmap, bsum2, grid, stream);
-    if (dw) return launch_a<true, false, PAIRED>(in, P, tmap, bsum2, grid, stream);
-    if (rgby) return launch_a<false, true, PAIRED>(in, P, tmap, bsum2, grid, stream);
-    return launch_a<false, false, PAIRED>(in, P, tmap, bsum2, grid, stream);
+    if (dw && rgby) return launch_a<TW, true, true, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    if (dw) return launch_a<TW, true, false, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    if (rgby) return launch_a<TW, false, true, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    return launch_a<TW, false, false, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+}
+
+template <int TW>
+static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int pairs, f2 *bsum2, float *orient,
+                        float *line_end, float *gray, int *winmax, cudaStream_t stream)
+{
+    const int h = S.a.h, w = S.a.w;
+    CUtensorMap map_x, map_b;
+    std::memset(&map_x, 0, sizeof(map_x));
+    std::memset(&map_b, 0, sizeof(map_b));
+    using TA = TileA<kTileHA, TW>;
+    S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
+    int rc = paired_in ? dispatch_a<TW, true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream)
+                       : dispatch_a<TW, false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream);
+    if (rc != SILENT_OK) return rc;
+    using TB = TileB<kTileHB, TW>;
+    constexpr int NT = ThreadsB<TW>::value;
+    auto kern = stack_b_kernel<kTileHB, TW, NT>;
+    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
+    S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
+    const dim3 grid(ceil_div(w, TW), ceil_div(h, kTileHB), pairs);
+    kern<<<grid, NT, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
+    SILENT_LAUNCH_CHECK("stack_b_kernel");
+    return SILENT_OK;
 }
 
 // pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
 // tensor of pyramid_pair_kernel with `pair_levels` levels per frame (images paired across consecutive frames).
+// winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
                 int *winmax, cudaStream_t stream)
@@ -836,23 +929,9 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     if (geo && winmax) S.b.win = *geo;
     S.a.pair_levels = S.b.pair_levels = levels;
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    const dim3 grid_a(ceil_div(w, kTileW), ceil_div(h, kTileHA), pairs);
-    const dim3 grid(ceil_div(w, kTileW), ceil_div(h, kTileHB), pairs);
-    CUtensorMap map_x, map_b;
-    std::memset(&map_x, 0, sizeof(map_x));
-    std::memset(&map_b, 0, sizeof(map_b));
-    using TA = TileA<kTileHA, kTileW>;
-    S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
-    rc = paired_in ? dispatch_a<true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, grid_a, stream)
-                   : dispatch_a<false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, grid_a, stream);
-    if (rc != SILENT_OK) return rc;
-    using TB = TileB<kTileHB, kTileW>;
-    auto kern = stack_b_kernel<kTileHB, kTileW, kThreadsB>;
-    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
-    S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
-    kern<<<grid, kThreadsB, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
-    SILENT_LAUNCH_CHECK("stack_b_kernel");
-    return SILENT_OK;
+    if (pick_tile_w(w) == 48)
+        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, stream);
+    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, stream);
 }
 
 }  // namespace silent
