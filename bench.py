@@ -215,14 +215,15 @@ def run_ours(args, rank, local_rank, world):
     # per-stage device time (separate, untimed pass with the library's event hooks)
     import ctypes
     _lib.check(_lib.lib().silent_plan_enable_timing(plan.handle, 1))
-    stage = np.zeros((5, 3))
+    stage = np.zeros((5, 5))
     for i in range(5):
         pipe.run_frames(frames, out=bufs)
-        vals = [ctypes.c_float() for _ in range(3)]
-        _lib.check(_lib.lib().silent_plan_stage_ms(plan.handle, *[ctypes.byref(v) for v in vals]))
+        vals = [ctypes.c_float() for _ in range(5)]
+        _lib.check(_lib.lib().silent_plan_stage_ms(plan.handle, *[ctypes.byref(v) for v in vals[:3]]))
+        _lib.check(_lib.lib().silent_plan_stack_split_ms(plan.handle, ctypes.byref(vals[3]), ctypes.byref(vals[4])))
         stage[i] = [v.value for v in vals]
     _lib.check(_lib.lib().silent_plan_enable_timing(plan.handle, 0))
-    stage_ms = stage[1:].mean(axis=0)
+    stage_ms = stage[1:].mean(axis=0)   # pyramid, stack (a + b), emit, stack_a, stack_b
 
     # end to end through the host-buffer entry point
     orient_host = torch.empty((n, h, w, 3), dtype=torch.float32).pin_memory().numpy()
@@ -256,6 +257,20 @@ def run_ours(args, rank, local_rank, world):
     achieved = alg_bytes * B / (ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     fps = world * B / (ms * 1e-3)
+    # per-kernel view: each kernel's own algorithmic bytes per frame = what it must read + write
+    level_bytes = L * h * w * 4
+    crop_bytes = alg_bytes - 2 * 3 * level_bytes
+    kernel_alg = {"pyramid_pair_kernel": crop_bytes + 3 * level_bytes,           # union crop in, planar pyramid out
+                  "stack_a_kernel": 3 * level_bytes + level_bytes,               # pyramid in, channel-sum plane out
+                  "stack_b_kernel": level_bytes + 2 * 3 * level_bytes + level_bytes}   # plane in; orient, line_end, gray out
+    kernel_ms = {"pyramid_pair_kernel": stage_ms[0], "stack_a_kernel": stage_ms[3], "stack_b_kernel": stage_ms[4]}
+    kernels = {}
+    for name, kb in kernel_alg.items():
+        gbs = kb * B / (kernel_ms[name] * 1e-3) / 1e9 if kernel_ms[name] > 0 else 0.0
+        kernels[name] = {"ms": float(kernel_ms[name]), "algorithmic_bytes_per_launch": int(kb * B), "achieved": gbs,
+                         "frac": gbs / peak, "share_of_step": float(kernel_ms[name] / max(stage_ms[:3].sum(), 1e-9)),
+                         "traffic": (traffic or {}).get("kernels", {}).get(name)}
+    dominant = max(kernel_ms, key=kernel_ms.get)
     h2d = B * FRAME_HW[0] * FRAME_HW[1] * 3
     d2h = 2 * n * h * w * 3 * 4 + 8 + 32 * len(res.points)
     line = {
@@ -275,10 +290,14 @@ def run_ours(args, rank, local_rank, world):
                 "api": "LineEndPipeline.run_host -> silent_pipeline_run_host, pinned host buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                     "kernel": "whole step (pyramid_kernel + stack_fused_kernel + emit kernels), per-GPU",
+                     "traffic": traffic.get("dram_bytes_per_step") if traffic else None,
+                     "kernel": "whole step per GPU: pyramid_pair_kernel + stack_a_kernel + stack_b_kernel + 4 emit "
+                               "kernels (the step's algorithmic bytes over the step's device time; dominant kernel: %s)"
+                               % dominant,
                      "algorithmic_bytes_per_step": alg_bytes * B, "peak_source": peak_src,
-                     "stage_ms": {"pyramid": stage_ms[0], "stack_fused": stage_ms[1], "emit": stage_ms[2]}},
+                     "traffic_source": traffic.get("source") if traffic else None,
+                     "stage_ms": {"pyramid": stage_ms[0], "stack_fused": stage_ms[1], "emit": stage_ms[2]},
+                     "kernels": kernels},
     }
     if args.batch1:
         one = frames[:1].contiguous()

@@ -163,6 +163,8 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
  * emit stages in milliseconds. */
 int silent_plan_enable_timing(silent_plan *plan, int enable);
 int silent_plan_stage_ms(silent_plan *plan, float *pyramid_ms, float *stack_ms, float *emit_ms);
+/* the fused stack's two kernels separately: x -> channel sum (stack_a) and channel sum -> outputs (stack_b) */
+int silent_plan_stack_split_ms(silent_plan *plan, float *stack_a_ms, float *stack_b_ms);
 
 /* Same, with HOST buffers on both sides: the drop-in for LineEndDisplayer.callback (recognition_testing.py:136-144):
  * frames_host [batch,H,W,frame_c] -> orient_host, line_end_host [batch*L,h,w,3], points_host [capacity][4], *count_host.

@@ -18,7 +18,7 @@ POST_NONE, POST_RELU, POST_RELU_CLIP = 0, 1, 2
 # every symbol include/silent_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "silent_abi_version", "silent_last_error", "silent_launch_count", "silent_device_count",
-    "silent_plan_enable_timing", "silent_plan_stage_ms", "silent_plan_create", "silent_plan_destroy",
+    "silent_plan_enable_timing", "silent_plan_stage_ms", "silent_plan_stack_split_ms", "silent_plan_create", "silent_plan_destroy",
     "silent_plan_reserve", "silent_plan_levels", "silent_plan_level_hw", "silent_plan_level_info",
     "silent_plan_level_tables", "silent_plan_algorithmic_bytes", "silent_pyramid_build", "silent_conv2d",
     "silent_regulate", "silent_pad_inwards", "silent_value_from_color", "silent_selection_workspace_bytes",
@@ -61,6 +61,7 @@ def lib():
         "silent_launch_count": (i64, []),
         "silent_plan_enable_timing": (i, [p, i]),
         "silent_plan_stage_ms": (i, [p, ctypes.POINTER(f), ctypes.POINTER(f), ctypes.POINTER(f)]),
+        "silent_plan_stack_split_ms": (i, [p, ctypes.POINTER(f), ctypes.POINTER(f)]),
         "silent_plan_create": (i, [ctypes.POINTER(SilentParams), ctypes.POINTER(p)]),
         "silent_plan_destroy": (None, [p]),
         "silent_plan_reserve": (i, [p, i]),

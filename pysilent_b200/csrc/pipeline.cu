@@ -61,6 +61,7 @@ silent_plan::~silent_plan()
 {
     for (cudaEvent_t e : ev)
         if (e) cudaEventDestroy(e);
+    if (ev_mid) cudaEventDestroy(ev_mid);
     release(ws);
     if (d_tables) cudaFree(d_tables);
     if (d_pair_words) cudaFree(d_pair_words);
@@ -133,7 +134,8 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
     return stack_fused(pyr, n, plan->h, plan->w, pair_path ? plan->levels : 0, W,
                        orient_dev ? orient_dev + img0 * level_elems * 3 : nullptr,
                        line_end_dev ? line_end_dev + img0 * level_elems * 3 : nullptr, ws.d_gray + img0 * level_elems,
-                       ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr, s);
+                       ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr, s,
+                       plan->timing ? plan->ev_mid : nullptr);
 }
 
 static int check_pipeline_args(const silent_plan *plan, const silent_stack_weights *W, const void *frames, int batch)
@@ -181,6 +183,7 @@ int silent_plan_enable_timing(silent_plan *plan, int enable)
     if (enable)
         for (cudaEvent_t &e : plan->ev)
             if (!e) SILENT_CUDA(cudaEventCreate(&e));
+    if (enable && !plan->ev_mid) SILENT_CUDA(cudaEventCreate(&plan->ev_mid));
     plan->timing = enable != 0;
     return SILENT_OK;
 }
@@ -199,11 +202,21 @@ int silent_plan_stage_ms(silent_plan *plan, float *pyramid_ms, float *stack_ms, 
 // Frames per chunk of the host-buffer pipeline: even (frame pairs), at most kMaxChunks chunks per call.
 static int host_chunk_frames(int batch)
 {
-    int per = (batch + 7) / 8;
+    int per = (batch + kMaxChunks - 1) / kMaxChunks;   // small chunks: the first download starts early
     per = std::max(per, 2);
     per += per & 1;
     while ((batch + per - 1) / per > kMaxChunks) per += 2;
     return per;
+}
+
+int silent_plan_stack_split_ms(silent_plan *plan, float *stack_a_ms, float *stack_b_ms)
+{
+    if (!plan) return fail(SILENT_E_INVAL, "null plan");
+    if (!plan->timing || !plan->ev[3] || !plan->ev_mid) return fail(SILENT_E_INVAL, "timing is not enabled on this plan");
+    SILENT_CUDA(cudaEventSynchronize(plan->ev[3]));
+    if (stack_a_ms) SILENT_CUDA(cudaEventElapsedTime(stack_a_ms, plan->ev[1], plan->ev_mid));
+    if (stack_b_ms) SILENT_CUDA(cudaEventElapsedTime(stack_b_ms, plan->ev_mid, plan->ev[2]));
+    return SILENT_OK;
 }
 
 int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_host,

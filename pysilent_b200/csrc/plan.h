@@ -67,6 +67,7 @@ struct silent_plan {
     silent::Workspace ws;
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // before pyramid / stack / emit, after emit
+    cudaEvent_t ev_mid = nullptr;                               // between the two stack kernels
 
     ~silent_plan();
 };

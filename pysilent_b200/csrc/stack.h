@@ -16,7 +16,7 @@ struct WindowGeom {
 size_t stack_workspace_bytes(int n, int h, int w);
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
-                int *winmax, cudaStream_t stream);
+                int *winmax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr);
 
 // pyramid.cu
 int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
