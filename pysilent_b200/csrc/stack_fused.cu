@@ -21,6 +21,7 @@
 // bit-identical to it. HBM-bound by design; tensor cores do not apply (3-channel fp32 stencils).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 
@@ -156,20 +157,28 @@ __device__ __forceinline__ void copy_out_tile(const float *__restrict__ stage, f
     }
 }
 
-// Same tile through the TMA unit: thread t < 2 * TH issues ONE bulk store of its staged row (needs 16-byte aligned rows:
-// w % 4 == 0). The caller fences + barriers before, and waits (bulk_wait_read) before the staging buffer is reused.
+// Same tile through the TMA unit: ONE bulk store per staged row (needs 16-byte aligned rows: w % 4 == 0). A warp issues
+// its lanes' bulk copies one after the other, so the 2 * TH rows are dealt to lanes 0..per_warp-1 of the warps
+// [warp0, warp0 + nwarps): with all warps of the CTA each one issues only a handful. The caller fences + barriers
+// before; every issuing thread commits its own group and must bulk_wait_read() before the staging buffer is reused.
 template <int TH, int TW>
-__device__ __forceinline__ void copy_out_rows_bulk(const float *__restrict__ stage, float *__restrict__ out, int img0,
-                                                   int img1, bool has_b, int ty0, int tx0, int h, int w, int tid)
+__device__ __forceinline__ bool copy_out_rows_bulk(const float *__restrict__ stage, float *__restrict__ out, int img0,
+                                                   int img1, bool has_b, int ty0, int tx0, int h, int w, int tid,
+                                                   int warp0, int nwarps)
 {
     constexpr int PITCH = TW * 3 + 4;
-    if (tid < 2 * TH) {
-        const int lane = tid / TH, r = tid - lane * TH, gy = ty0 + r;
+    const int per_warp = (2 * TH + nwarps - 1) / nwarps;
+    const int wi = (tid >> 5) - warp0, ln = tid & 31;
+    if (wi < 0 || wi >= nwarps || ln >= per_warp) return false;
+    const int row = wi * per_warp + ln;
+    if (row < 2 * TH) {
+        const int lane = row / TH, r = row - lane * TH, gy = ty0 + r;
         if (gy < h && (lane == 0 || has_b))
-            bulk_store(out + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3, stage + (size_t)tid * PITCH,
+            bulk_store(out + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3, stage + (size_t)row * PITCH,
                        (uint32_t)(min(TW, w - tx0) * 3 * sizeof(float)));
-        bulk_commit();
     }
+    bulk_commit();
+    return true;
 }
 
 __device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[kPX])
@@ -244,10 +253,11 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
 
     if (PAIRED_IN && P.use_tma) {
         // ---- load x: the planes are already pair-interleaved; one TMA box [3 planes][X_ROWS][X_PITCH] -------------------
-        if (tid == 0) mbar_init(&tma_bar, 1);
-        __syncthreads();
-        if (tid == 0)
+        if (tid == 0) {   // requested before the barrier that publishes the mbarrier to the other threads
+            mbar_init(&tma_bar, 1);
             tma_load_box3(sX, &tmap, 2 * (tx0 - 2), ty0 - 2, 3 * pair, &tma_bar, (uint32_t)(3 * T::X_PLANE * sizeof(f2)));
+        }
+        __syncthreads();
         mbar_wait(&tma_bar, 0);
     } else if (PAIRED_IN) {
         // ---- same tile with plain 128-bit loads (= 2 pixels x 2 frames), zero outside the level ------------------------
@@ -466,10 +476,11 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
 
     // ---- load the channel-sum tile (pairs are already interleaved): one TMA box [B_ROWS][B_PITCH], zero outside -------
     if (P.use_tma) {
-        if (tid == 0) mbar_init(&tma_bar, 1);
-        __syncthreads();
-        if (tid == 0)
+        if (tid == 0) {   // the copy is requested before the barrier that publishes the mbarrier to the other threads
+            mbar_init(&tma_bar, 1);
             tma_load_box3(sB, &tmap, 2 * (tx0 - 4), ty0 - 5, pair, &tma_bar, (uint32_t)(T::B_PLANE * sizeof(f2)));
+        }
+        __syncthreads();
         mbar_wait(&tma_bar, 0);
     } else {
         constexpr int QUADS = T::B_PITCH / 2;
@@ -615,6 +626,8 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     // ---- orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5) and hand
     //      the rows to the TMA unit; the copy drains while S5 computes -----------------------------------------------
     const bool bulk_ok = (w % 4) == 0;   // staged rows start and end on 16-byte boundaries of the global tensors
+    constexpr int kS5Warps = (TH * T::E_RUNS + 31) / 32, kIdleWarps = NT / 32 - kS5Warps;
+    bool issued_orient = false, issued_line_end = false;
     if (orient) {
         for (int t = tid; t < TH * T::E_RUNS; t += NT) {
             const int r = t % TH, k = t / TH;
@@ -631,8 +644,9 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
         }
         fence_async_smem();
         __syncthreads();
-        if (bulk_ok) {
-            copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
+        if (bulk_ok) {   // by the warps that have no S5 task (if any), so that no S5 worker starts late
+            issued_orient = copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid,
+                                                       kIdleWarps ? kS5Warps : 0, kIdleWarps ? kIdleWarps : NT / 32);
         } else {
             copy_out_tile<TH, TW, NT>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
         }
@@ -665,7 +679,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     }
     // the staging buffer is free again once the orient rows have been read out
     if (orient) {
-        if (bulk_ok && tid < 2 * TH) bulk_wait_read();
+        if (issued_orient) bulk_wait_read();
         __syncthreads();
     }
     int best0 = 0, best1 = 0;
@@ -751,7 +765,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     __syncthreads();
     if (line_end) {
         if (bulk_ok) {
-            copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
+            issued_line_end = copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid, 0, NT / 32);
         } else {
             copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
         }
@@ -763,7 +777,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
                 atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], sWin[tid]);
         }
     }
-    if (line_end && bulk_ok && tid < 2 * TH) bulk_wait_read();   // the CTA's shared memory must outlive the reads
+    if (issued_line_end) bulk_wait_read();   // the CTA's shared memory must outlive the reads
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
