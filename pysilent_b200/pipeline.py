@@ -18,7 +18,24 @@ from .constant_convolutions.center_surround import midget_rgc, rgby_3
 from .constant_convolutions.edge_orientation_detector import rgb_2d_stripe_tensors
 from .constant_convolutions.gaussian_blur.gaussian_blur import blur_tensor
 from .constant_convolutions.oriented_end_detector import rgb_2d_end_tensors
-from .util.zoom.from_image import get_plan
+from .util.zoom.from_image import PyramidPlan
+
+def orientation_bank_filters(n_orient=8):
+    """Filters of BASELINE config C4: ``n_orient`` orientations at ``k * 360 / n_orient`` degrees built
+    with the reference's per-vector generators (``stripe_tensor`` ``stripe_tensor.py:21-70``, ``end_tensor``
+    ``oriented_end_detector.py:13-55``, ``blur_tensor`` ``gaussian_blur.py:13-54``). The generators only build square
+    channel maps, so the stripe bank is ``[3,3,n,n]`` sliced to its first 3 input channels (the rgby output feeds it)."""
+    from .constant_convolutions.edge_orientation_detector.stripe_tensor import stripe_tensor
+    from .constant_convolutions.oriented_end_detector import end_tensor
+    vecs = [np.array([np.cos(k * 2 * np.pi / n_orient), np.sin(k * 2 * np.pi / n_orient)]) for k in range(n_orient)]
+    eye = np.eye(n_orient)
+    spread = [1, 1, 1] + [0] * (n_orient - 3)
+    stripe = sum(stripe_tensor(v, spread, list(eye[k] * 4), spread, list(-eye[k] * 4)) for k, v in enumerate(vecs))
+    end = sum(end_tensor(3 * v, list(eye[k]), list(.25 * eye[k]), list(eye[k]), list(.5 * eye[k]))
+              for k, v in enumerate(vecs))
+    return dict(rgc=midget_rgc(2), rgby=rgby_3(2), stripe=np.ascontiguousarray(stripe[:, :, :3, :]),
+                blur=blur_tensor(2, 7, channels_in=n_orient, channels_out=n_orient), end=end)
+
 
 LineEndResult = collections.namedtuple("LineEndResult", "orient padded_line_end gray points")
 LineEndResult.__doc__ = """orient: ``orient_tensor`` [N,h,w,3]; padded_line_end: ``padded_line_end_tensor`` [N,h,w,3];
@@ -32,7 +49,10 @@ class LineEndPipeline:
     ``(w, h)`` of every pyramid level, ``zoom_ratio`` the scale between levels.
     """
 
-    def __init__(self, n_dimensions=2, output_size=(288, 192), output_colors=3, zoom_ratio=math.e ** .5, device=None):
+    def __init__(self, n_dimensions=2, output_size=(288, 192), output_colors=3, zoom_ratio=math.e ** .5, device=None,
+                 orientations=None):
+        self.orientations = orientations   # None: the reference's 3 simplex orientations (fused kernels); n: config C4
+        self._bank = None
         self.output_size = tuple(output_size)
         self.output_colors = output_colors
         self.zoom_ratio = zoom_ratio
@@ -42,6 +62,7 @@ class LineEndPipeline:
         self.device = torch.device(device) if device is not None else None
         self._weights = None
         self._weights_key = None
+        self._plans = {}   # per instance: a plan owns workspace buffers, so pipelines (cameras, threads) never share one
 
     # -- weights ------------------------------------------------------------------------------------------------------
     def filters(self):
@@ -71,6 +92,8 @@ class LineEndPipeline:
     # -- graph on a pyramid (LineEndDisplayer.run) --------------------------------------------------------------------
     def run(self, pyramid_tensor, want_points=True):
         """S1-S8 on a pyramid ``[N, h, w, 3]`` (numpy or CUDA tensor). One fused kernel + the emit kernels."""
+        if self.orientations is not None:
+            return self.run_bank(pyramid_tensor, want_points)
         if self.blur_size != 7:
             return self.run_unfused(pyramid_tensor, want_points)
         orient, line_end, gray = _ops.stack_fused(pyramid_tensor, self.stack_weights())
@@ -93,10 +116,43 @@ class LineEndPipeline:
         points = max_value_indices_region(padded, self.region_shape, gray) if want_points else None
         return LineEndResult(orient, padded, gray, points)
 
+    def bank_filters(self):
+        if self._bank is None:
+            self._bank = orientation_bank_filters(self.orientations)
+        return self._bank
+
+    def run_bank(self, pyramid_tensor, want_points=True):
+        """Config C4: S1-S2 on 3 channels, S3-S7 on an ``orientations``-channel bank, through the per-operator kernels
+        (same composition as ``compile()``, ``recognition_testing.py:69-77``)."""
+        from .util.selection import pad_inwards, max_value_indices_region
+        from .util.color import get_value_from_color
+        from .util.regulator import regulate_tensor
+        f = self.bank_filters()
+        x = _ops.as_device_tensor(pyramid_tensor)
+        x = _ops.conv2d(_ops.conv2d(x, f["rgc"], post=_lib.POST_RELU), f["rgby"], post=_lib.POST_RELU)
+        orient = regulate_tensor(_ops.conv2d(x, f["stripe"], post=_lib.POST_RELU), f["blur"], 1.0, .1)
+        line_end = _ops.conv2d(orient, f["end"], post=_lib.POST_RELU_CLIP, clip_max=255.0)
+        padded = pad_inwards(line_end, [[0, 0], [2, 2], [2, 2], [0, 0]])
+        gray = get_value_from_color(padded)
+        region = [1, self.region_shape[1], self.region_shape[2], self.orientations]
+        points = max_value_indices_region(padded, region, gray) if want_points else None
+        return LineEndResult(orient, padded, gray, points)
+
     # -- frames resident in HBM ---------------------------------------------------------------------------------------
+    def _plan(self, frame_shape, frame_dtype, device):
+        """Plan cache keyed like the reference's per-shape session (``recognition_testing.py:108-118``). The cache is
+        per pipeline: use one ``LineEndPipeline`` per camera thread, as the reference uses one displayer per camera."""
+        key = (tuple(int(v) for v in frame_shape), frame_dtype, self.output_colors, self.output_size,
+               float(self.zoom_ratio), str(device))
+        plan = self._plans.get(key)
+        if plan is None:
+            with torch.cuda.device(device):
+                plan = PyramidPlan(frame_shape, frame_dtype, self.output_colors, self.output_size, self.zoom_ratio)
+            self._plans[key] = plan
+        return plan
+
     def plan_for(self, frames):
-        return get_plan(frames.shape[1:], frames.dtype, self.output_colors, self.output_size, self.zoom_ratio,
-                        frames.device)
+        return self._plan(frames.shape[1:], frames.dtype, frames.device)
 
     def run_frames(self, frames, want_points=True, points_capacity=None, out=None):
         """frames: CUDA ``[B, H, W, 3]`` uint8/float32 -> LineEndResult over ``B * L`` levels (pyramid + S1-S8).
@@ -106,6 +162,10 @@ class LineEndPipeline:
         """
         frames = frames if frames.dim() == 4 else frames.unsqueeze(0)
         frames = frames.contiguous()
+        if self.orientations is not None:   # C4: pyramid kernel, then the orientation bank operator by operator
+            from .util.zoom.from_image import image_to_zoom_tensor
+            return self.run_bank(image_to_zoom_tensor(frames, self.output_colors, self.output_size, self.zoom_ratio),
+                                 want_points)
         plan = self.plan_for(frames)
         b = int(frames.shape[0])
         plan.reserve(b)
@@ -144,7 +204,7 @@ class LineEndPipeline:
             frames = frames.astype(np.float32)
         dev = self._device()
         tdtype = torch.uint8 if frames.dtype == np.uint8 else torch.float32
-        plan = get_plan(frames.shape[1:], tdtype, self.output_colors, self.output_size, self.zoom_ratio, dev)
+        plan = self._plan(frames.shape[1:], tdtype, dev)
         b = frames.shape[0]
         n = b * plan.levels
         if orient_out is None:

@@ -321,3 +321,120 @@ def test_pipeline_properties_at_full_size(default_filters):
     assert float(p.max()) <= 255.0 and float(p.min()) >= 0.0 and float(full.orient.min()) >= 0.0
     from pysilent_b200.util.selection import pad_inwards
     assert torch.equal(pad_inwards(p, [[0, 0], [2, 2], [2, 2], [0, 0]]), p)
+
+
+# ---- BASELINE config C4: 8-orientation bank, 8-level 4K pyramid ----------------------------------------------------------
+
+def _oracle_bank(c_oracle, pyr, f, region):
+    a = c_oracle.conv2d(c_oracle.conv2d(pyr, f["rgc"], post=1), f["rgby"], post=1)
+    orient = c_oracle.regulate_tensor(c_oracle.conv2d(a, f["stripe"], post=1), f["blur"], 1.0, .1)
+    line_end = c_oracle.conv2d(orient, f["end"], post=2, clip_hi=255.0)
+    padded = c_oracle.pad_inwards(line_end, [[0, 0], [2, 2], [2, 2], [0, 0]])
+    gray = c_oracle.get_value_from_color(padded)
+    points, _ = c_oracle.max_value_indices_region(gray, region)
+    return dict(orient=orient, padded=padded, gray=gray, points=points)
+
+
+def test_orientation_bank_config4_bit_exact(c_oracle, goldens):
+    """C4's filter bank (8 orientations: stripe 3->8, blur 8->8, end 8->8) on a small frame: every stage bit-equal to the
+    C oracle composed operator by operator, bank weights equal to the reference generators' own output."""
+    from oracle import silent_oracle as lit
+    from pysilent_b200 import LineEndPipeline
+    pipe = LineEndPipeline(output_size=(96, 64), zoom_ratio=2 ** .5, orientations=8)
+    f = pipe.bank_filters()
+    G = goldens["generators"]
+    assert np.array_equal(f["stripe"], G["stripe_8"][:, :, :3, :]) and np.array_equal(f["end"], G["end_8"])
+    assert np.array_equal(f["blur"], G["blur_8"])
+    frames = np.stack([structured_frame(70 + i, 300, 420) for i in range(2)])
+    pyr = c_oracle.from_image(frames, 3, (96, 64), 2 ** .5)
+    ref = _oracle_bank(c_oracle, pyr, f, (32, 48))
+    res = pipe.run_frames(torch.from_numpy(frames).cuda())
+    assert tuple(res.orient.shape) == pyr.shape[:3] + (8,)
+    _check_stack(res, ref, None, "config 4 bank")
+    lit_orient = lit.regulate_tensor(lit.conv_relu(lit.conv_relu(lit.conv_relu(pyr, f["rgc"]), f["rgby"]), f["stripe"]),
+                                     f["blur"], 1.0, .1)
+    assert_close(res.orient, lit_orient, "config 4 orient literal", tol=2e-5)
+
+
+def test_orientation_bank_config4_full_size_properties():
+    """C4 at its named shape (3840x2160, scale sqrt2 -> 8 levels, 8 orientations): level count, batch independence,
+    determinism, value ranges, sorted point rows."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(4, i, 2160, 3840) for i in range(2)])
+    pipe = LineEndPipeline(zoom_ratio=2 ** .5, orientations=8)
+    dev = torch.from_numpy(frames).cuda()
+    full = pipe.run_frames(dev)
+    assert tuple(full.orient.shape) == (16, 192, 288, 8) and tuple(full.padded_line_end.shape) == (16, 192, 288, 8)
+    one = pipe.run_frames(dev[1:2])
+    assert torch.equal(one.orient, full.orient[8:]) and torch.equal(one.padded_line_end, full.padded_line_end[8:])
+    again = pipe.run_frames(dev)
+    assert torch.equal(again.padded_line_end, full.padded_line_end) and torch.equal(again.points, full.points)
+    p = full.padded_line_end
+    assert float(p[:, :2].abs().max()) == 0 and float(p[:, :, -2:].abs().max()) == 0
+    assert float(p.max()) <= 255.0 and float(p.min()) >= 0.0 and float(full.orient.min()) >= 0.0
+    pts = full.points.cpu().numpy()
+    key = (pts[:, 0] * 192 + pts[:, 1]) * 288 + pts[:, 2]
+    assert len(pts) > 0 and (np.diff(key) > 0).all()
+
+
+# ---- BASELINE config C5: many 720p streams; host-buffer entry point from several camera threads --------------------------
+
+def test_multi_stream_config5_chunked_host_path(c_oracle, default_filters):
+    """C5 shape (1280x720, 5 levels): a batch of streams through the chunked, overlapped host-buffer call equals the
+    device-resident call and the oracle, for batches that do and do not fill whole chunks (odd batch: a lone frame in
+    the last pair)."""
+    from pysilent_b200 import LineEndPipeline
+    pipe = LineEndPipeline(zoom_ratio=2 ** .5)
+    frames = np.stack([synthetic_frame(5, i, 720, 1280) for i in range(37)])
+    dev = pipe.run_frames(torch.from_numpy(frames).cuda())
+    host = pipe.run_host(frames)
+    assert np.array_equal(host.orient, dev.orient.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(host.padded_line_end, dev.padded_line_end.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(host.points, dev.points.cpu().numpy())
+    pyr, ref = _oracle_pipeline(c_oracle, frames[35:37], (288, 192), 2 ** .5, default_filters)
+    L = pyr.shape[0] // 2
+    assert np.array_equal(host.orient[35 * L:], ref["orient"], equal_nan=True)
+    sel = host.points[host.points[:, 0] >= 35 * L].copy()
+    sel[:, 0] -= 35 * L
+    assert np.array_equal(sel, ref["points"])
+    pinned = torch.from_numpy(frames[:6]).pin_memory()
+    o = torch.empty((6 * L, 192, 288, 3), dtype=torch.float32).pin_memory()
+    l = torch.empty_like(o).pin_memory()
+    part = pipe.run_host(pinned.numpy(), o.numpy(), l.numpy())
+    assert np.array_equal(part.orient, host.orient[:6 * L], equal_nan=True)
+    assert np.array_equal(part.padded_line_end, host.padded_line_end[:6 * L], equal_nan=True)
+
+
+def test_callback_from_camera_threads(c_oracle, default_filters):
+    """The reference calls ``callback`` on one thread per camera: concurrent calls from non-main threads,
+    one pipeline per camera, give the single-threaded results."""
+    import threading
+    from pysilent_b200 import LineEndPipeline
+    frames = [synthetic_frame(1, i, 480, 640) for i in range(4)]
+    want = []
+    for fr in frames:
+        _, ref = _oracle_pipeline(c_oracle, fr[None], (288, 192), 1.3, default_filters)
+        want.append(ref)
+    got = [None] * 4
+    errors = []
+
+    def camera(i):
+        try:
+            torch.cuda.set_device(0)
+            pipe = LineEndPipeline(zoom_ratio=1.3)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(3):
+                    got[i] = pipe.callback(frames[i], cam_id=i)
+        except Exception as exc:   # surfaced below: an exception in a thread would otherwise pass silently
+            errors.append(exc)
+
+    threads = [threading.Thread(target=camera, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(4):
+        assert np.array_equal(np.stack(got[i][1]), want[i]["orient"], equal_nan=True)
+        assert np.array_equal(np.stack(got[i][2]), want[i]["padded"], equal_nan=True)
+        assert np.array_equal(got[i][3], want[i]["points"])
