@@ -138,6 +138,40 @@ int silent_top_value_points(const float *color_dev, const float *value_dev, int 
                             double top_percent, float *out_dev, void *workspace_dev, size_t workspace_bytes,
                             silent_stream stream);
 
+/* ---- display tensors that follow gray_line_end_tensor (recognition_testing.py:79-100) --------------------------------- */
+
+/* get_centroids(value_tensor, region_shape) / get_centroids_array (util/centroids.py:21-71): per region_h x region_w
+ * block (stride = region, SAME) the value-weighted mean index (x, y) -> corrected_dev [n,oh,ow,2] and the block totals
+ * -> total_dev [n,oh,ow,1], oh = ceil(h / region_h); then, if centroids_dev is not NULL, the L1 distance of every pixel
+ * to the centroid of its (nearest-upsampled) block -> centroids_dev [n,h,w,1]. value_dev is [n,h,w,1]. */
+int silent_get_centroids(const float *value_dev, int n, int h, int w, int region_h, int region_w, float *corrected_dev,
+                         float *total_dev, float *centroids_dev, silent_stream stream);
+
+/* tf.image.resize_nearest_neighbor(x, (out_h, out_w)) (align_corners False; recognition_testing.py:83). */
+int silent_resize_nearest(const float *x_dev, int n, int h, int w, int c, int out_h, int out_w, float *out_dev,
+                          silent_stream stream);
+
+/* get_boosting(input, exhaustion_tensor, exhaustion_max, excitation_max, ...) (util/energy/boosting.py:10-42): 3 x 3
+ * max-pool equality on input ** energy -> fired_dev [n,h,w,1] (1 / 0); energy_dev [n,h,w,1] (the tf.Variable) is
+ * updated in place: clip((energy * 255 - fired * 255 + recovery) / 255, -exhaustion_max, excitation_max).
+ * recovery_mode (util/energy/recovery.py:12-22): 1 constant, 2 input based, 3 both. scratch_dev: [n,h,w] floats. */
+int silent_get_boosting(const float *input_dev, float *energy_dev, int n, int h, int w, float exhaustion_max,
+                        float excitation_max, int recovery_mode, float *fired_dev, float *scratch_dev,
+                        silent_stream stream);
+
+/* The scalar arithmetic between those operators (recognition_testing.py:79-100, boosting.py:36-39), one rounding per
+ * written operation. y_dev is only read by SILENT_PW_PRODUCT. */
+enum {
+    SILENT_PW_DIV255 = 0,          /* x / 255.0                       gray / 255.0, :79 */
+    SILENT_PW_INVERT255 = 1,       /* 255 - x * 255                   255 - centroids * 255, :98 */
+    SILENT_PW_IMPORTANCE = 2,      /* clip(x * (255 / 4.0), 1, 256) - 1                      :81 */
+    SILENT_PW_MUL255 = 3,          /* x * 255                         fired_importants * 255, :98 */
+    SILENT_PW_ENERGY_DISPLAY = 4,  /* x * 127.5 + 127.5               boosting.py:37-39 with both maxima 1 */
+    SILENT_PW_PRODUCT = 5          /* x * y                           has_fired * input, boosting.py:36 */
+};
+int silent_pointwise(const float *x_dev, const float *y_dev, size_t count, int kind, float *out_dev,
+                     silent_stream stream);
+
 /* ---- fused path ---------------------------------------------------------------------------------------------------- */
 
 /* S1-S7 of LineEndDisplayer.compile (recognition_testing.py:69-77) fused into two kernels (cut at the one-channel

@@ -69,6 +69,14 @@ def lib():
         L.so_line_end_stack.restype = None
         L.so_line_end_stack.argtypes = [_f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p, c_int, _f32p] + \
             [_f32p] * 8
+        L.so_get_centroids.restype = None
+        L.so_get_centroids.argtypes = [_f32p, c_int, c_int, c_int, c_int, c_int, _f32p, _f32p, _f32p]
+        L.so_resize_nearest.restype = None
+        L.so_resize_nearest.argtypes = [_f32p, c_int, c_int, c_int, c_int, c_int, c_int, _f32p]
+        L.so_get_boosting.restype = None
+        L.so_get_boosting.argtypes = [_f32p, _f32p, c_int, c_int, c_int, c_float, c_float, c_int, _f32p, _f32p]
+        L.so_pointwise.restype = None
+        L.so_pointwise.argtypes = [_f32p, _f32p, c_size, c_int, _f32p]
         _lib = L
     return _lib
 
@@ -190,3 +198,62 @@ def line_end_stack(pyramid, weights, region_divisor=2.0):
     pts, count = max_value_indices_region(gray, (int(h / region_divisor), int(w / region_divisor)))
     bufs.update(gray=gray, points=pts)
     return bufs
+
+
+# ---- "next" rows: centroids, nearest resize, boosting, display arithmetic ------------------------------------------------
+
+def _same_out(n, s):
+    return -(-n // s)
+
+
+def get_centroids(value, region_shape):
+    """-> (centroids [N,h,w,1], total_pool [N,oh,ow,1], corrected [N,oh,ow,2]) (util/centroids.py:21-71)."""
+    value = _c(value)
+    n, h, w = value.shape[:3]
+    rh, rw = int(region_shape[1]), int(region_shape[2])
+    oh, ow = _same_out(h, rh), _same_out(w, rw)
+    corrected = np.empty((n, oh, ow, 2), np.float32)
+    total = np.empty((n, oh, ow, 1), np.float32)
+    cent = np.empty((n, h, w, 1), np.float32)
+    with np.errstate(all="ignore"):
+        lib().so_get_centroids(value, n, h, w, rh, rw, corrected, total, cent)
+    return cent, total, corrected
+
+
+def resize_nearest(x, size):
+    x = _c(x)
+    n, h, w, c = x.shape
+    out = np.empty((n, int(size[0]), int(size[1]), c), np.float32)
+    lib().so_resize_nearest(x, n, h, w, c, int(size[0]), int(size[1]), out)
+    return out
+
+
+def get_boosting(inp, energy, exhaustion_max=1.0, excitation_max=1.0, recovery_mode=1):
+    """-> (has_fired, new_energy); ``energy`` is not modified."""
+    inp, energy = _c(inp), _c(energy).copy()
+    n, h, w = inp.shape[:3]
+    fired = np.empty_like(inp)
+    scratch = np.empty_like(inp)
+    lib().so_get_boosting(inp, energy, n, h, w, exhaustion_max, excitation_max, recovery_mode, fired, scratch)
+    return fired, energy
+
+
+def pointwise(x, kind, y=None):
+    x = _c(x)
+    out = np.empty_like(x)
+    lib().so_pointwise(x, _c(y) if y is not None else x, x.size, kind, out)
+    return out
+
+
+def display_tensors(orient, padded, gray, energy):
+    """recognition_testing.py:77-100 in the canonical order: the six fetched tensors and the new boosting state."""
+    scaled = pointwise(gray, 0)
+    centroids, total, _ = get_centroids(scaled, (1, 3, 3))
+    importances = pointwise(total, 2)
+    half = (np.asarray(gray.shape[1:3], dtype=np.float32) / np.float32(np.e ** .5)).astype(np.int32)
+    im2 = resize_nearest(gray, half)
+    centroids2, _, _ = get_centroids(pointwise(im2, 0), (1, 3, 3))
+    fired, new_energy = get_boosting(importances, energy)
+    fired_rgb = np.repeat(pointwise(pointwise(fired, 5, importances), 3), 3, axis=-1)
+    update_rgb = np.repeat(pointwise(new_energy, 4), 3, axis=-1)
+    return [orient, pointwise(centroids, 1), pointwise(centroids2, 1), fired_rgb, update_rgb, padded], new_energy

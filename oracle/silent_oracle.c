@@ -363,3 +363,132 @@ void so_line_end_stack(const float *pyr, int N, int h, int w, const float *rgc, 
     so_pad_inwards(line_end, N, h, w, 3, 2, 2, 2, 2, padded);
     so_value_from_color(padded, (size_t)N * h * w, 3, gray);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------- */
+/* "next" rows: centroids (util/centroids.py:21-71), nearest resize, boosting (util/energy/boosting.py)  */
+/*                                                                                                                  */
+/* Canonical order: block sums are float32 add chains from +0 over the window in (ky, kx) order (out-of-image taps    */
+/* contribute nothing); biased = index * value is one float32 multiply; centroid = sum / total and distances are      */
+/* IEEE float32 divide / subtract / fabsf, summed as (|dx| + |dy|); the boosting update is the float32 sequence       */
+/* ((e * 255 - exhaustion) + recovery) / 255 then max(lo) then min(hi), NaN-propagating; pow is canon_pow.            */
+/* ---------------------------------------------------------------------------------------------------------------- */
+
+static int nearest_src_f(int dst, int n_in, int n_out)
+{
+    float scale = (float)((double)n_in / (double)n_out);
+    int s = (int)floorf((float)dst * scale);
+    return s < n_in - 1 ? s : n_in - 1;
+}
+
+/* corrected: [N][oh][ow][2] = (cx, cy); total: [N][oh][ow]; centroids: [N][h][w] (may be NULL) */
+void so_get_centroids(const float *value, int N, int h, int w, int rh, int rw, float *corrected, float *total,
+                      float *centroids)
+{
+    int oh, ow, pt, pl;
+    same_geometry(h, rh, rh, &oh, &pt);
+    same_geometry(w, rw, rw, &ow, &pl);
+    for (int n = 0; n < N; ++n) {
+        const float *v = value + (size_t)n * h * w;
+        for (int i = 0; i < oh; ++i)
+            for (int j = 0; j < ow; ++j) {
+                float sx = 0.0f, sy = 0.0f, st = 0.0f;
+                for (int ky = 0; ky < rh; ++ky) {
+                    int y = i * rh - pt + ky;
+                    if (y < 0 || y >= h) continue;
+                    for (int kx = 0; kx < rw; ++kx) {
+                        int x = j * rw - pl + kx;
+                        if (x < 0 || x >= w) continue;
+                        float val = v[(size_t)y * w + x];
+                        sx = sx + (float)x * val;
+                        sy = sy + (float)y * val;
+                        st = st + val;
+                    }
+                }
+                size_t o = ((size_t)n * oh + i) * ow + j;
+                corrected[2 * o] = sx / st;
+                corrected[2 * o + 1] = sy / st;
+                total[o] = st;
+            }
+        if (!centroids) continue;
+        for (int y = 0; y < h; ++y) {
+            int i = nearest_src_f(y, oh, h);
+            for (int x = 0; x < w; ++x) {
+                int j = nearest_src_f(x, ow, w);
+                size_t o = ((size_t)n * oh + i) * ow + j;
+                float dx = fabsf(corrected[2 * o] - (float)x), dy = fabsf(corrected[2 * o + 1] - (float)y);
+                centroids[((size_t)n * h + y) * w + x] = dx + dy;
+            }
+        }
+    }
+}
+
+void so_resize_nearest(const float *x, int N, int h, int w, int c, int oh, int ow, float *out)
+{
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < oh; ++y) {
+            int sy = nearest_src_f(y, h, oh);
+            for (int xx = 0; xx < ow; ++xx) {
+                int sx = nearest_src_f(xx, w, ow);
+                for (int ch = 0; ch < c; ++ch)
+                    out[(((size_t)n * oh + y) * ow + xx) * c + ch] = x[(((size_t)n * h + sy) * w + sx) * c + ch];
+            }
+        }
+}
+
+static float nan_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+/* recovery_mode: 1 constant (10), 2 input based (0.8 * fire strength), 3 both (max). energy is updated in place. */
+void so_get_boosting(const float *inp, float *energy, int N, int h, int w, float exhaustion_max, float excitation_max,
+                     int recovery_mode, float *fired, float *biased_scratch)
+{
+    size_t plane = (size_t)h * w;
+    for (size_t i = 0; i < (size_t)N * plane; ++i) biased_scratch[i] = so_canon_pow(inp[i], energy[i]);
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const float *b = biased_scratch + (size_t)n * plane;
+                size_t o = (size_t)n * plane + (size_t)y * w + x;
+                int first = 1;
+                float m = 0.0f;
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        int yy = y + dy, xx = x + dx;
+                        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+                        float v = b[(size_t)yy * w + xx];
+                        m = first ? v : nan_max(m, v);
+                        first = 0;
+                    }
+                float f = (b[(size_t)y * w + x] == m) ? 1.0f : 0.0f;
+                float strength = f * inp[o];
+                float exhaustion = f * 255.0f;
+                float recovery = 10.0f;
+                if (recovery_mode == 2) recovery = strength * 0.8f;
+                if (recovery_mode == 3) recovery = nan_max(strength * 0.8f, 10.0f);
+                float t = energy[o] * 255.0f;
+                t = t - exhaustion;
+                t = t + recovery;
+                t = t / 255.0f;
+                t = t < -exhaustion_max ? -exhaustion_max : t;
+                t = t > excitation_max ? excitation_max : t;
+                fired[o] = f;
+                energy[o] = t;
+            }
+}
+
+/* display arithmetic of recognition_testing.py:79-100. kind: 0 x / 255; 1 255 - x * 255; 2 clip(x * 63.75, 1, 256) - 1;
+ * 3 x * 255; 4 x * 127.5 + 127.5 (two roundings); 5 a * b (fired * importance) with b = second input */
+void so_pointwise(const float *x, const float *y, size_t count, int kind, float *out)
+{
+    for (size_t i = 0; i < count; ++i) {
+        float v = x[i], r;
+        switch (kind) {
+            case 0: r = v / 255.0f; break;
+            case 1: { float t = v * 255.0f; r = 255.0f - t; } break;
+            case 2: { float t = v * 63.75f; t = t < 1.0f ? 1.0f : t; t = t > 256.0f ? 256.0f : t; r = t - 1.0f; } break;
+            case 3: r = v * 255.0f; break;
+            case 4: { float t = v * 127.5f; r = t + 127.5f; } break;
+            default: r = v * y[i]; break;
+        }
+        out[i] = r;
+    }
+}

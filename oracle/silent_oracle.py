@@ -268,3 +268,112 @@ def line_end_stack(pyramid, weights, region_divisor=2.0):
     region = [1, int(h / region_divisor), int(w / region_divisor), ch]  # :40
     pts = max_value_indices_region(p, region, g)                        # :90-91
     return dict(rgc=a, rgby=b, stripe=c, orient=d, line_end=e, padded=p, gray=g, points=pts)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# "Next" rows: centroids, boosting, the six display tensors of LineEndDisplayer.compile
+# ----------------------------------------------------------------------------------------------------------------------
+
+
+def index_tensor(h, w):
+    """util/index_tensor.py:7-20 with ``are_dimensions_reversed``: ``ind[y, x] = (x, y)``, cast to float32."""
+    ind = np.empty((h, w, 2), dtype=np.float32)
+    ind[..., 0] = np.arange(w, dtype=np.float32)[np.newaxis, :]
+    ind[..., 1] = np.arange(h, dtype=np.float32)[:, np.newaxis]
+    return ind
+
+
+def _strided_window_sum(x, rh, rw):
+    """``tf.nn.convolution(x, ones, strides=[rh, rw], 'SAME')`` per channel: float64 sums over each window."""
+    n, h, w, c = x.shape
+    oh, pt = _same_geometry(h, rh, rh)
+    ow, pl = _same_geometry(w, rw, rw)
+    out = np.zeros((n, oh, ow, c), dtype=np.float64)
+    for i in range(oh):
+        ya, yb = max(i * rh - pt, 0), min(i * rh - pt + rh, h)
+        for j in range(ow):
+            xa, xb = max(j * rw - pl, 0), min(j * rw - pl + rw, w)
+            out[:, i, j, :] = x[:, ya:yb, xa:xb, :].astype(np.float64).sum(axis=(1, 2))
+    return out
+
+
+def get_centroids_array(value, region_shape):
+    """util/centroids.py:49-71: per ``region`` block, the value-weighted mean index ``(x, y)``; also the block totals."""
+    value = np.asarray(value, dtype=np.float32)
+    n, h, w, _ = value.shape
+    rh, rw = int(region_shape[1]), int(region_shape[2])
+    ind = index_tensor(h, w)
+    biased = (ind[np.newaxis] * value).astype(np.float32)                       # :35  ind * to_channels(value, 2)
+    centroid_pool = _strided_window_sum(biased, rh, rw).astype(np.float32)      # :36-39 identity 'additive' filter
+    # :40-43: every tap weighs both (identical) channels by 1/2 -> the plain window sum of the value
+    total_pool = _strided_window_sum(value, rh, rw).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        corrected = (centroid_pool / total_pool).astype(np.float32)             # :44 (0 / 0 = NaN on empty blocks)
+    return corrected, total_pool
+
+
+def get_centroids(value, region_shape):
+    """util/centroids.py:21-46 -> (L1 distance of every pixel to its block's centroid ``[N,h,w,1]``, block totals)."""
+    value = np.asarray(value, dtype=np.float32)
+    n, h, w, _ = value.shape
+    corrected, total_pool = get_centroids_array(value, region_shape)
+    resized = corrected[:, nearest_index(h, corrected.shape[1])][:, :, nearest_index(w, corrected.shape[2])]   # :45
+    dist = np.abs(resized - index_tensor(h, w)[np.newaxis]).astype(np.float32)  # :46 math.equality_distance
+    return (dist[..., 0] + dist[..., 1])[..., np.newaxis].astype(np.float32), total_pool
+
+
+def resize_nearest_neighbor(x, size):
+    """``tf.image.resize_nearest_neighbor`` (align_corners False)."""
+    return x[:, nearest_index(int(size[0]), x.shape[1])][:, :, nearest_index(int(size[1]), x.shape[2])]
+
+
+def max_pool_3x3(x):
+    """``tf.nn.max_pool(x, (1,3,3,1), (1,1,1,1), 'SAME')``, NaN-propagating."""
+    n, h, w, c = x.shape
+    out = np.empty_like(x)
+    for i in range(h):
+        for j in range(w):
+            out[:, i, j, :] = np.max(x[:, max(i - 1, 0):i + 2, max(j - 1, 0):j + 2, :], axis=(1, 2))
+    return out
+
+
+def get_boosting(inp, energy, exhaustion_max=1, excitation_max=1, input_based_recovery=False, constant_recovery=True):
+    """util/energy/boosting.py:10-42 (+ recovery.py:4-22). Returns (has_fired, new_energy); the caller keeps the state."""
+    inp = np.asarray(inp, dtype=np.float32)
+    energy = np.asarray(energy, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        biased = np.power(inp.astype(np.float64), energy.astype(np.float64)).astype(np.float32)   # :17
+    pooled = max_pool_3x3(biased)                                                                  # :18
+    fired = np.where(biased == pooled, np.float32(1), np.float32(0))                               # :20-22
+    strength = (fired * inp).astype(np.float32)                                                    # :24
+    exhaustion = (fired * np.float32(255.0)).astype(np.float32)                                    # :26
+    if input_based_recovery and not constant_recovery:
+        recovery = (strength * np.float32(0.8)).astype(np.float32)
+    elif constant_recovery and not input_based_recovery:
+        recovery = np.full_like(strength, 10)
+    elif input_based_recovery and constant_recovery:
+        recovery = np.maximum((strength * np.float32(0.8)).astype(np.float32), np.full_like(strength, 10))
+    else:
+        raise ValueError("You must choose a type of recovery")
+    t = (((energy * np.float32(255.0)).astype(np.float32) - exhaustion).astype(np.float32) + recovery).astype(np.float32)
+    t = (t / np.float32(255.0)).astype(np.float32)                                                 # :30-33
+    new_energy = np.minimum(np.maximum(t, np.float32(-exhaustion_max)), np.float32(excitation_max))
+    return fired, new_energy.astype(np.float32)
+
+
+def display_tensors(orient, padded, gray, energy, centroid_region=(1, 3, 3)):
+    """recognition_testing.py:77-100: the six tensors ``run()`` fetches, and the boosting state after this frame."""
+    scaled = (gray / np.float32(255.0)).astype(np.float32)
+    centroids, importances = get_centroids(scaled, centroid_region)                                 # :79-80
+    importances = (np.minimum(np.maximum((importances * np.float32(255 / 4.0)).astype(np.float32), np.float32(1)),
+                              np.float32(256)) - np.float32(1)).astype(np.float32)                  # :81
+    half = (np.asarray(gray.shape[1:3], dtype=np.float32) / np.float32(np.e ** .5)).astype(np.int32)   # :82
+    im2 = resize_nearest_neighbor(gray, half)                                                       # :83
+    centroids2, _ = get_centroids((im2 / np.float32(255.0)).astype(np.float32), centroid_region)    # :84
+    fired, new_energy = get_boosting(importances, energy)                                           # :86-87
+    fired_rgb = np.repeat((fired * importances).astype(np.float32), 3, axis=-1)                     # boosting.py:36
+    update_rgb = np.repeat((new_energy * np.float32(127.5) + np.float32(127.5)).astype(np.float32), 3, axis=-1)   # :37-39
+    outs = [orient, (np.float32(255) - centroids * np.float32(255)).astype(np.float32),
+            (np.float32(255) - centroids2 * np.float32(255)).astype(np.float32),
+            (fired_rgb * np.float32(255)).astype(np.float32), update_rgb, padded]                   # :98-100
+    return outs, new_energy

@@ -46,6 +46,9 @@ class Shape(tuple):
     def as_list(self):
         return list(self)
 
+    def concatenate(self, other):
+        return Shape(list(self) + [int(d) for d in other])
+
 
 TensorShape = Shape
 
@@ -58,6 +61,12 @@ class Tensor:
 
     def numpy(self):
         return self._v
+
+    def set_shape(self, shape):   # static-shape hint in TF: nothing to do for an eager array
+        assert tuple(int(d) for d in shape) == self._v.shape, (tuple(shape), self._v.shape)
+
+    def value(self):
+        return Tensor(self._v)
 
     @property
     def shape(self):
@@ -204,6 +213,61 @@ def abs(x):  # noqa: A001
     return Tensor(np.abs(_arr(x)))
 
 
+class Variable(Tensor):
+    """``tf.Variable``: a tensor with state; ``assign`` stores and returns the new value."""
+
+    def __init__(self, initial_value, dtype=None, **kw):
+        a = _arr(initial_value)
+        super().__init__(a.astype(dtype) if dtype is not None else a.copy())
+
+    def assign(self, value):
+        self._v = _arr(value).astype(self._v.dtype)
+        return Tensor(self._v)
+
+
+def convolution(input=None, filter=None, strides=None, padding="SAME", **kw):  # noqa: A002
+    """``tf.nn.convolution`` for NHWC rank-4 input: ``strides`` lists the SPATIAL strides only."""
+    sp = [1, 1] if strides is None else [int(v) for v in strides]
+    return conv2d(input=input, filter=filter, strides=(1, sp[0], sp[1], 1), padding=padding)
+
+
+def less_equal(x, y):
+    with np.errstate(invalid="ignore"):
+        return Tensor(_arr(x) <= _arr(y))
+
+
+# ---- tensorflow.python.ops.array_ops / framework.ops symbols used by util/color/to_channels.py --------------------------
+class _NameScope:
+    def __init__(self, name, default_name=None, values=None):
+        self.name = name or default_name
+
+    def __enter__(self):
+        return self.name
+
+    def __exit__(self, *exc):
+        return False
+
+
+def convert_to_tensor(x, name=None, **kw):
+    return x if isinstance(x, Tensor) else Tensor(np.asarray(x))
+
+
+def rank(x):
+    return Tensor(np.asarray(_arr(x).ndim, dtype=np.int32))
+
+
+def expand_dims(x, axis):
+    return Tensor(np.expand_dims(_arr(x), int(axis)))
+
+
+def concat(values, axis=0, **kw):
+    return Tensor(np.concatenate([np.atleast_1d(_arr(v)) for v in values], axis=int(axis)))
+
+
+def tile(x, multiples, name=None):
+    return Tensor(np.tile(_arr(x), tuple(int(m) for m in _arr(multiples).reshape(-1))))
+
+
 def _same_geometry(n, k, s):
     out = -(-n // s)
     pad_total = max((out - 1) * s + k - n, 0)
@@ -256,7 +320,7 @@ class _ResizeMethod:
 
 def _resize_nearest(images, size, **kw):
     x = _arr(images)
-    oh, ow = (int(s) for s in size)
+    oh, ow = (int(s) for s in _arr(size).reshape(-1))
     h, wd = x.shape[1:3]
     ys = np.minimum(np.floor(np.arange(oh, dtype=np.float32) * np.float32(h / oh)).astype(np.int64), h - 1)
     xs = np.minimum(np.floor(np.arange(ow, dtype=np.float32) * np.float32(wd / ow)).astype(np.int64), wd - 1)
@@ -280,9 +344,10 @@ def install():
     tf.__silent_shim__ = True
     for name in ("Tensor", "TensorShape", "float32", "int32", "int64", "constant", "cast", "shape", "ones", "ones_like",
                  "zeros_like", "pad", "reduce_sum", "maximum", "minimum", "clip_by_value", "pow", "greater_equal",
-                 "equal", "where", "abs"):
+                 "equal", "where", "abs", "Variable"):
         setattr(tf, name, globals()[name])
-    tf.nn = types.SimpleNamespace(conv2d=conv2d, max_pool=max_pool)
+    tf.nn = types.SimpleNamespace(conv2d=conv2d, max_pool=max_pool, convolution=convolution)
+    tf.math = types.SimpleNamespace(less_equal=less_equal)
     tf.image = types.SimpleNamespace(resize_images=resize_images, resize_nearest_neighbor=_resize_nearest,
                                      ResizeMethod=_ResizeMethod, grayscale_to_rgb=grayscale_to_rgb)
     mods = {"tensorflow": tf}
@@ -291,6 +356,10 @@ def install():
         m = types.ModuleType("tensorflow." + sub)
         mods["tensorflow." + sub] = m
     mods["tensorflow.python.framework.dtypes"].int32 = np.int32
+    for name in ("expand_dims", "rank", "ones", "concat", "tile"):
+        setattr(mods["tensorflow.python.ops.array_ops"], name, globals()[name])
+    mods["tensorflow.python.framework.ops"].name_scope = _NameScope
+    mods["tensorflow.python.framework.ops"].convert_to_tensor = convert_to_tensor
     for full, m in mods.items():
         sys.modules[full] = m
         if "." in full:

@@ -10,3 +10,4 @@ from .constant_convolutions.center_surround import center_surround_tensor  # noq
 from .constant_convolutions.edge_orientation_detector import stripe_tensor, simplex_stripe_tensors  # noqa: F401
 from .util import zoom  # noqa: F401
 from .pipeline import LineEndPipeline  # noqa: F401
+from .recognition_testing import LineEndDisplayer  # noqa: F401

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsilent_b200.so")
 
 SILENT_U8, SILENT_F32 = 0, 1
 POST_NONE, POST_RELU, POST_RELU_CLIP = 0, 1, 2
+PW_DIV255, PW_INVERT255, PW_IMPORTANCE, PW_MUL255, PW_ENERGY_DISPLAY, PW_PRODUCT = range(6)
 
 # every symbol include/silent_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
@@ -23,7 +24,7 @@ SYMBOLS = (
     "silent_plan_level_tables", "silent_plan_algorithmic_bytes", "silent_pyramid_build", "silent_conv2d",
     "silent_regulate", "silent_pad_inwards", "silent_value_from_color", "silent_selection_workspace_bytes",
     "silent_max_value_indices_region", "silent_top_value_points", "silent_stack_workspace_bytes", "silent_stack_fused", "silent_pipeline_run",
-    "silent_pipeline_run_host",
+    "silent_pipeline_run_host", "silent_get_centroids", "silent_resize_nearest", "silent_get_boosting", "silent_pointwise",
 )
 
 
@@ -82,6 +83,10 @@ def lib():
         "silent_stack_fused": (i, [p, i, i, i, ctypes.POINTER(SilentStackWeights), p, p, p, p, sz, p]),
         "silent_pipeline_run": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, p, i64, p, p]),
         "silent_pipeline_run_host": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, i64, p, p]),
+        "silent_get_centroids": (i, [p, i, i, i, i, i, p, p, p, p]),
+        "silent_resize_nearest": (i, [p, i, i, i, i, i, i, p, p]),
+        "silent_get_boosting": (i, [p, p, i, i, i, f, f, i, p, p, p]),
+        "silent_pointwise": (i, [p, p, sz, i, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

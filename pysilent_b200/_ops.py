@@ -150,6 +150,60 @@ def top_value_points(color, value, top_percent):
     return out
 
 
+def get_centroids(value, region_h, region_w, want_distance=True):
+    """-> (centroids [n,h,w,1] or None, total_pool [n,oh,ow,1], corrected_pool [n,oh,ow,2])."""
+    v = as_device_tensor(value)
+    n, h, w, c = _nhwc(v, "get_centroids")
+    if c != 1:
+        raise ValueError("value tensor must have one channel")
+    oh, ow = -(-h // region_h), -(-w // region_w)
+    corrected = torch.empty((n, oh, ow, 2), dtype=torch.float32, device=v.device)
+    total = torch.empty((n, oh, ow, 1), dtype=torch.float32, device=v.device)
+    cent = torch.empty((n, h, w, 1), dtype=torch.float32, device=v.device) if want_distance else None
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().silent_get_centroids(ptr(v), n, h, w, region_h, region_w, ptr(corrected), ptr(total),
+                                                   ptr(cent), stream_ptr()), "silent_get_centroids")
+    return cent, total, corrected
+
+
+def resize_nearest(tensor, out_h, out_w):
+    x = as_device_tensor(tensor)
+    n, h, w, c = _nhwc(x, "resize_nearest_neighbor")
+    out = torch.empty((n, int(out_h), int(out_w), c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().silent_resize_nearest(ptr(x), n, h, w, c, int(out_h), int(out_w), ptr(out), stream_ptr()),
+                   "silent_resize_nearest")
+    return out
+
+
+def boosting(inp, energy, exhaustion_max, excitation_max, recovery_mode):
+    """Updates ``energy`` (CUDA float32, same shape as ``inp``) in place; returns has_fired."""
+    x = as_device_tensor(inp)
+    n, h, w, c = _nhwc(x, "get_boosting")
+    if c != 1 or tuple(energy.shape) != tuple(x.shape) or not energy.is_cuda or energy.dtype != torch.float32 \
+            or not energy.is_contiguous():
+        raise ValueError("exhaustion tensor must be a contiguous CUDA float32 tensor shaped like the one-channel input")
+    fired = torch.empty_like(x)
+    scratch = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().silent_get_boosting(ptr(x), ptr(energy), n, h, w, float(exhaustion_max),
+                                                  float(excitation_max), int(recovery_mode), ptr(fired), ptr(scratch),
+                                                  stream_ptr()), "silent_get_boosting")
+    return fired
+
+
+def pointwise(x, kind, y=None):
+    x = as_device_tensor(x)
+    y = as_device_tensor(y) if y is not None else None
+    if y is not None and y.shape != x.shape:
+        raise ValueError("pointwise product needs equal shapes, got %s and %s" % (tuple(x.shape), tuple(y.shape)))
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().silent_pointwise(ptr(x), ptr(y), x.numel(), int(kind), ptr(out), stream_ptr()),
+                   "silent_pointwise")
+    return out
+
+
 def stack_fused(pyramid, weights, want_orient=True, want_line_end=True, want_gray=True):
     x = as_device_tensor(pyramid)
     n, h, w, c = _nhwc(x, "stack_fused")

@@ -15,7 +15,8 @@ What is executed, unmodified, from ``/root/reference/slam_recognition``:
   zero-filled so the uninitialised tail rows/columns (``from_image.py:53``) are defined as 0;
 * the filter callables and selection ops (``filters/*.py``, ``util/apply_filter.py``, ``util/regulator``,
   ``util/selection``, ``util/color/get_value.py``) composed in the order of ``recognition_testing.py:69-77,90-91`` ->
-  ``stack.npz``. TensorFlow 1.x is not installable here, so these run on ``oracle/tf1_shim.py``, an eager numpy
+  ``stack.npz``; and ``util/centroids.py`` + ``util/energy/boosting.py`` composed as ``recognition_testing.py:49-57,
+  77-100`` for three consecutive frames -> ``display.npz``. TensorFlow 1.x is not installable here, so these run on ``oracle/tf1_shim.py``, an eager numpy
   restatement of the ~25 TF-1 symbols they call. Results at that boundary are therefore "parity unpinned" against real
   TensorFlow; the composition, constants and weights are the reference's own.
 
@@ -233,10 +234,49 @@ def make_stacks(sr):
     return out
 
 
+def reference_display(padded, gray, steps=3):
+    """recognition_testing.py:49-57 (pre_compile: the boosting state) and :77-100 (compile) on the reference's own
+    ``get_centroids`` / ``get_boosting``, fed the same padded/gray tensors ``steps`` times (a still camera): the six
+    fetched tensors of every step and the state after it."""
+    import math as m
+    tf = sys.modules["tensorflow"]
+    get_centroids = importlib.import_module("slam_recognition.util").get_centroids
+    boosting = importlib.import_module("slam_recognition.util.energy.boosting")
+    gray_t = tf.constant(gray, dtype=tf.float32)
+    centroid_region_shape = [1, 3, 3]
+    _, imp0 = get_centroids(gray_t / 255.0, centroid_region_shape, debug=True)
+    energy_values = boosting.initialize_boosting(imp0 * 255)
+    out = []
+    for _ in range(steps):
+        centroids, centroid_importances = get_centroids(gray_t / 255.0, centroid_region_shape, debug=True)
+        centroid_importances = tf.clip_by_value(centroid_importances * (255 / 4.0), 1, 256) - 1
+        half_shape = tf.cast(gray_t.shape[1:3], tf.float32) / tf.constant(m.e ** .5)
+        im2 = tf.image.resize_nearest_neighbor(gray_t, tf.cast(half_shape, tf.int32))
+        centroids2, _ = get_centroids(im2 / 255.0, centroid_region_shape, debug=True)
+        fired_importants, update_importances = boosting.get_boosting(centroid_importances, energy_values,
+                                                                     for_visualizing=True)
+        out.append(dict(centroids=(255 - centroids * 255).numpy(), centroids2=(255 - centroids2 * 255).numpy(),
+                        fired=(fired_importants * 255).numpy(), update=update_importances.numpy(),
+                        energy=energy_values.numpy().copy()))
+    return out
+
+
+def make_display(stacks):
+    out = {}
+    for name in ("noise", "natural", "flat"):
+        steps = reference_display(stacks[name + "_padded"], stacks[name + "_gray"])
+        for i, st in enumerate(steps):
+            for k, v in st.items():
+                out["%s_step%d_%s" % (name, i, k)] = v.astype(np.float32)
+        print("display", name, "fired pixels per step", [int((st["fired"] > 0).sum()) for st in steps])
+    np.savez_compressed(os.path.join(HERE, "display.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
     sr = import_reference()
     g = make_generators(sr)
     print("generators:", len(g))
     p = make_pyramids(sr)
     print("pyramids:", [k for k in p if k.endswith("_pyramid")], [p[k].shape for k in p if k.endswith("_pyramid")])
-    make_stacks(sr)
+    make_display(make_stacks(sr))

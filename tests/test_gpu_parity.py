@@ -33,12 +33,16 @@ def assert_bits(actual, expected, what):
         what, (~same).sum(), same.size, np.nanmax(np.abs(a - e)))
 
 
-def assert_close(actual, expected, what, tol=REL_TOL):
+def assert_close(actual, expected, what, tol=REL_TOL, scale=None):
+    """``scale``: magnitude of the OPERANDS when the result is a difference of much larger quantities (centroid
+    distances are |centroid index - pixel index| with indices up to the level width)."""
     a = actual.detach().cpu().numpy() if isinstance(actual, torch.Tensor) else np.asarray(actual)
     e = np.asarray(expected)
     assert a.shape == e.shape, (what, a.shape, e.shape)
     assert np.array_equal(np.isnan(a), np.isnan(e)), "%s: NaN masks differ" % what
     peak = np.nanmax(np.abs(e)) if np.isfinite(e).any() else 1.0
+    if scale is not None:
+        peak = max(peak, scale)
     err = np.nanmax(np.abs(a - e)) if np.isfinite(e).any() else 0.0
     assert err <= tol * max(peak, 1e-30), "%s: max |d| = %g > %g * peak %g" % (what, err, tol, peak)
 
@@ -438,3 +442,111 @@ def test_callback_from_camera_threads(c_oracle, default_filters):
         assert np.array_equal(np.stack(got[i][1]), want[i]["orient"], equal_nan=True)
         assert np.array_equal(np.stack(got[i][2]), want[i]["padded"], equal_nan=True)
         assert np.array_equal(got[i][3], want[i]["points"])
+
+
+# ---- centroids, boosting, the reference driver's six display tensors -------------------------------
+
+def test_centroids_resize_boosting_operators_bit_exact(c_oracle):
+    from oracle import silent_oracle as lit
+    from pysilent_b200.util import get_centroids
+    from pysilent_b200.util.centroids import get_centroids_array
+    from pysilent_b200.util.energy import get_boosting, initialize_boosting
+    from pysilent_b200 import _ops
+    rs = np.random.RandomState(51)
+    for n, h, w, region in ((2, 12, 18, [1, 3, 3]), (3, 13, 17, [1, 3, 3]), (1, 116, 174, [1, 3, 3]), (2, 20, 31, [1, 2, 4])):
+        v = rs.rand(n, h, w, 1).astype(np.float32)
+        v[0, :5, :7] = 0                                # empty blocks: 0 / 0 = NaN centroids
+        cent, total = get_centroids(v, region)
+        want_c, want_t, want_arr = c_oracle.get_centroids(v, region)
+        assert_bits(cent, want_c, "get_centroids %s" % ((n, h, w),))
+        assert_bits(total, want_t, "total_pool")
+        assert_bits(get_centroids_array(v, region), want_arr, "get_centroids_array")
+        lit_c, lit_t = lit.get_centroids(v, region)
+        assert np.isnan(lit_c).any()
+        assert_close(cent, lit_c, "get_centroids literal", scale=max(h, w))
+        assert_close(total, lit_t, "total_pool literal")
+        assert_bits(_ops.resize_nearest(v, 7, 11), c_oracle.resize_nearest(v, (7, 11)), "resize_nearest")
+        assert_bits(_ops.resize_nearest(v, 7, 11), lit.resize_nearest_neighbor(v, (7, 11)), "resize_nearest literal")
+    with pytest.raises(ValueError):
+        get_centroids(v, [1, 2.5, 3])
+    # boosting: five frames of a still camera, then a changed input; all three recovery selections
+    imp = (rs.rand(2, 16, 24, 1) * 60).astype(np.float32)
+    imp[1, 4:9, 4:9] = 0
+    for kw, mode in ((dict(), 1), (dict(input_based_recovery=True, constant_recovery=False), 2),
+                     (dict(input_based_recovery=True), 3)):
+        energy = initialize_boosting(imp)
+        e_ref = np.full_like(imp, 8)
+        e_lit = e_ref.copy()
+        for step in range(6):
+            x = imp if step < 4 else imp[:, ::-1].copy()
+            fired, state = get_boosting(x, energy, **kw)
+            f_ref, e_ref = c_oracle.get_boosting(x, e_ref, recovery_mode=mode)
+            assert state is energy
+            assert_bits(fired, f_ref, "has_fired step %d mode %d" % (step, mode))
+            assert_bits(energy, e_ref, "energy step %d mode %d" % (step, mode))
+            f_lit, e_lit = lit.get_boosting(x, e_lit, **kw)
+            assert_bits(fired, f_lit, "has_fired literal")
+            assert_close(energy, e_lit, "energy literal")
+    with pytest.raises(ValueError):
+        get_boosting(imp, energy, input_based_recovery=False, constant_recovery=False)
+
+
+def test_displayer_matches_reference_goldens(goldens, c_oracle):
+    """The six fetched tensors of three consecutive frames on the reference's golden pyramids.
+
+    (a) ``LineEndDisplayer.run`` (pyramid -> everything) bitwise against the C oracle. (b) The display operators fed the
+    GOLDEN gray / padded tensors against the reference's own centroid / boosting code executed on the TF-1 shim
+    (tests/golden/display.npz), to the north-star tolerance with identical fired cells. (b) isolates the display
+    operators: a block centroid sum(idx * v) / sum(v) is ill-conditioned where a block is almost empty, so float32
+    rounding noise of the upstream filter stack (1e-5 of its peak) may move such centroids arbitrarily."""
+    from pysilent_b200 import LineEndDisplayer
+    S = goldens["stack"]
+    D = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "display.npz"))
+    for name in ("noise", "natural", "flat"):
+        pyr = S[name + "_pyramid"]
+        disp = LineEndDisplayer(output_size=(pyr.shape[2], pyr.shape[1]))
+        iso = LineEndDisplayer(output_size=(pyr.shape[2], pyr.shape[1]))
+        ref = c_oracle.line_end_stack(pyr, disp.filters())
+        energy = np.full((pyr.shape[0], -(-pyr.shape[1] // 3), -(-pyr.shape[2] // 3), 1), 8, np.float32)
+        g_orient, g_padded, g_gray = (torch.from_numpy(S[name + k]).cuda() for k in ("_orient", "_padded", "_gray"))
+        for step in range(3):
+            got = disp.run(pyr)
+            want, energy = c_oracle.display_tensors(ref["orient"], ref["padded"], ref["gray"], energy)
+            assert len(got) == 6
+            for i, (g, wv) in enumerate(zip(got, want)):
+                assert_bits(g, wv, "%s step %d tensor %d" % (name, step, i))
+            got_iso = iso.display_tensors(g_orient, g_padded, g_gray)
+            for key, i in (("centroids", 1), ("centroids2", 2), ("fired", 3), ("update", 4)):
+                gold = D["%s_step%d_%s" % (name, step, key)]
+                assert_close(got_iso[i], gold, "%s step %d %s vs reference code" % (name, step, key),
+                             scale=255.0 * max(pyr.shape[1:3]) if key.startswith("centroids") else None)
+            assert np.array_equal(got_iso[3].cpu().numpy() > 0, D["%s_step%d_fired" % (name, step)] > 0)
+            assert_close(iso.energy_values, D["%s_step%d_energy" % (name, step)], "energy vs reference code")
+
+
+def test_displayer_callback_structure_and_state(c_oracle, default_filters):
+    """callback(frame, cam_id) returns ``[frame] + 6 lists of per-level images`` (recognition_testing.py:144); the
+    boosting state persists across frames and is reset when the frame shape changes; display() scales by 1/255."""
+    from pysilent_b200 import LineEndDisplayer
+    disp = LineEndDisplayer(zoom_ratio=1.3)
+    frame = synthetic_frame(1, 0, 480, 640)
+    pyr, ref = _oracle_pipeline(c_oracle, frame[None], (288, 192), 1.3, default_filters)
+    L = pyr.shape[0]
+    energy = np.full((L, 64, 96, 1), 8, np.float32)
+    for step in range(2):
+        out = disp.callback(frame, cam_id=0)
+        want, energy = c_oracle.display_tensors(ref["orient"], ref["padded"], ref["gray"], energy)
+        assert out[0] is frame and len(out) == 7 and all(len(out[1 + x]) == L for x in range(6))
+        for x in range(6):
+            assert_bits(np.stack(out[1 + x]), want[x], "callback step %d tensor %d" % (step, x))
+    assert out[1][0].shape == (192, 288, 3) and out[2][0].shape == (192, 288, 1) and out[3][0].shape == (116, 174, 1)
+    assert out[4][0].shape == (64, 96, 3) and out[5][0].shape == (64, 96, 3)
+    small = synthetic_frame(1, 1, 360, 480)
+    disp.callback(small)
+    assert tuple(disp.energy_values.shape)[0] != L or float(disp.energy_values.max()) <= 1.0
+    _, ref_s = _oracle_pipeline(c_oracle, small[None], (288, 192), 1.3, default_filters)
+    e0 = np.full((ref_s["gray"].shape[0], 64, 96, 1), 8, np.float32)
+    want_s, e1 = c_oracle.display_tensors(ref_s["orient"], ref_s["padded"], ref_s["gray"], e0)
+    assert_bits(disp.energy_values, e1, "state re-initialised on shape change")
+    shown = disp.display(small)
+    assert len(shown) == 7 and float(np.nanmax(shown[6])) <= 1.0

@@ -119,3 +119,48 @@ def test_emit_edge_cases(c_oracle):
 def test_synthetic_frames_are_deterministic():
     a, b = synthetic_frame(2, 7, 48, 64), synthetic_frame(2, 7, 48, 64)
     assert a.dtype == np.uint8 and np.array_equal(a, b) and not np.array_equal(a, synthetic_frame(2, 8, 48, 64))
+
+
+# ---- centroids / boosting / display tensors --------------------------------------------------------
+
+def test_display_oracles_equal_reference_centroid_and_boosting_code(goldens, c_oracle):
+    """tests/golden/display.npz was produced by the reference's util/centroids.py + util/energy/boosting.py (on the TF-1
+    shim) for three consecutive frames; both oracles reproduce it from the same gray / padded tensors: the literal one
+    bit for bit, the bit-defined C one to the north-star tolerance with identical fired cells."""
+    import os
+    from conftest import GOLDEN
+    S, D = goldens["stack"], np.load(os.path.join(GOLDEN, "display.npz"))
+    for name in ("noise", "natural", "flat"):
+        gray, padded, orient = S[name + "_gray"], S[name + "_padded"], S[name + "_orient"]
+        n, h, w, _ = gray.shape
+        e_c = np.full((n, -(-h // 3), -(-w // 3), 1), 8, np.float32)
+        e_l = e_c.copy()
+        for step in range(3):
+            outs_c, e_c = c_oracle.display_tensors(orient, padded, gray, e_c)
+            outs_l, e_l = lit.display_tensors(orient, padded, gray, e_l)
+            for key, i in (("centroids", 1), ("centroids2", 2), ("fired", 3), ("update", 4)):
+                gold = D["%s_step%d_%s" % (name, step, key)]
+                assert np.array_equal(outs_l[i], gold, equal_nan=True), (name, step, key)
+                assert np.array_equal(np.isnan(outs_c[i]), np.isnan(gold))
+                scale = 255.0 * max(h, w) if key.startswith("centroids") else np.nanmax(np.abs(gold))
+                assert np.nanmax(np.abs(outs_c[i] - gold)) <= 1e-5 * scale, (name, step, key)
+            assert np.array_equal(outs_c[3] > 0, D["%s_step%d_fired" % (name, step)] > 0)
+            assert np.array_equal(e_l, D["%s_step%d_energy" % (name, step)])
+            assert np.abs(e_c - e_l).max() <= 1e-6
+        assert (e_l < 1).any() and (e_l == 1).any()      # some cells fired and are exhausted, the rest recovered fully
+
+
+def test_index_tensor_reference_kat():
+    """The reference's tests/test_index_tensor.py:10-24: element [y, x] of the index tensor is (x, y)."""
+    from pysilent_b200.util import index_tensor
+    want = [[[0, 0], [1, 0]], [[0, 1], [1, 1]]]
+    assert index_tensor.from_shape([4, 2, 2, 3]).tolist() == want
+    assert index_tensor.from_tensor(np.ones((4, 2, 2, 3))).tolist() == want
+    assert np.array_equal(lit.index_tensor(2, 2), np.asarray(want, np.float32))
+
+
+def test_recovery_selection_like_reference():
+    from pysilent_b200.util.energy import recovery_mode
+    assert (recovery_mode(False, True), recovery_mode(True, False), recovery_mode(True, True)) == (1, 2, 3)
+    with pytest.raises(ValueError):
+        recovery_mode(False, False)
