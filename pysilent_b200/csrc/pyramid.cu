@@ -176,6 +176,21 @@ __global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __g
     }
     __syncthreads();
 
+    // ---- the coarsest level is the first reader of a frame pair (finer levels then hit L2): ask L2 for the same tile of
+    //      the NEXT pair now, one bulk prefetch per (tap row, frame), so that CTA finds its rows in L2 instead of HBM --
+    const int wlo_pf = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2);
+    const int nw_pf = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2 + 1);
+    if (level == P.L - 1 && 2 * (q + 1) < P.B && nw_pf > 0) {
+        for (int i = tid; i < 2 * th * kTaps; i += kPairThreads) {
+            const int e = i >> 1, f = 2 * (q + 1) + (i & 1);
+            const int row = sTy[e];
+            if (row >= 0 && f < P.B) {
+                const uint8_t *src = P.frames + (size_t)f * frame_bytes + (size_t)row * P.row_bytes + (size_t)wlo_pf * 4;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nw_pf * 4) : "memory");
+            }
+        }
+    }
+
     // ---- phase V: column sums over the 6 y-taps, 16 byte-columns (one aligned 128-bit load per tap row and frame) per
     //      task: 12 independent 16-byte loads in flight per thread cover the HBM/L2 latency ---------------------------
     const int wlo = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2);   // multiples of 4 words

@@ -198,6 +198,7 @@ struct ParamsA {
     int h, w, n;      // level shape, number of images
     int pair_levels;  // image pairing: pair p holds images (a, a + pair_levels), see pair_images()
     int use_tma;      // PAIRED_IN only: load the tile with one TMA box copy
+    int prefetch_pairs;   // L2 prefetch distance in image pairs (0: off)
 };
 
 // Which two images ride in the float2 lanes of pair p. With pair_levels = 1 these are images (2p, 2p + 1); the
@@ -256,6 +257,12 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
         if (tid == 0) {   // requested before the barrier that publishes the mbarrier to the other threads
             mbar_init(&tma_bar, 1);
             tma_load_box3(sX, &tmap, 2 * (tx0 - 2), ty0 - 2, 3 * pair, &tma_bar, (uint32_t)(3 * T::X_PLANE * sizeof(f2)));
+            // the same tile of a pair that is scheduled a few waves from now: pull it from HBM into L2 meanwhile
+            const int kPrefetchPairs = P.prefetch_pairs;
+            if (kPrefetchPairs > 0 && pair + kPrefetchPairs < (int)gridDim.z)
+                asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tmap),
+                             "r"(2 * (tx0 - 2)), "r"(ty0 - 2), "r"(3 * (pair + kPrefetchPairs))
+                             : "memory");
         }
         __syncthreads();
         mbar_wait(&tma_bar, 0);
@@ -909,6 +916,7 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
     std::memset(&map_x, 0, sizeof(map_x));
     std::memset(&map_b, 0, sizeof(map_b));
     using TA = TileA<kTileHA, TW>;
+    S.a.prefetch_pairs = 8;   // ~ the image pairs whose tiles are resident on the chip at once
     S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
     int rc = paired_in ? dispatch_a<TW, true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream)
                        : dispatch_a<TW, false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream);
