@@ -631,12 +631,16 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     __syncthreads();
 
     // ---- orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5) and hand
-    //      the rows to the TMA unit; the copy drains while S5 computes -----------------------------------------------
+    //      the rows to the TMA unit. When the CTA has at least two warps WITHOUT an S5 task (S5 has the fewest tasks of
+    //      the three phases) they do all of this on their own, synchronised by a named barrier, while the S5 warps start
+    //      the end filter at once; the copy drains while S5 computes ---------------------------------------------
     const bool bulk_ok = (w % 4) == 0;   // staged rows start and end on 16-byte boundaries of the global tensors
     constexpr int kS5Warps = (TH * T::E_RUNS + 31) / 32, kIdleWarps = NT / 32 - kS5Warps;
+    constexpr bool kSideRestage = kIdleWarps >= 2;
+    constexpr int kRestageFirst = kSideRestage ? 32 * kS5Warps : 0, kRestageThreads = kSideRestage ? 32 * kIdleWarps : NT;
     bool issued_orient = false, issued_line_end = false;
-    if (orient) {
-        for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+    if (orient && tid >= kRestageFirst) {
+        for (int t = tid - kRestageFirst; t < TH * T::E_RUNS; t += kRestageThreads) {
             const int r = t % TH, k = t / TH;
             f2 d[kPX][3];
 #pragma unroll
@@ -650,12 +654,16 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             store_nhwc8<1>(sStage + (size_t)(TH + r) * T::ST_PITCH + 3 * kPX * k, d, true, kPX);
         }
         fence_async_smem();
-        __syncthreads();
-        if (bulk_ok) {   // by the warps that have no S5 task (if any), so that no S5 worker starts late
-            issued_orient = copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid,
-                                                       kIdleWarps ? kS5Warps : 0, kIdleWarps ? kIdleWarps : NT / 32);
+        if (kSideRestage) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kRestageThreads) : "memory");   // only the restaging warps
         } else {
-            copy_out_tile<TH, TW, NT>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid);
+            __syncthreads();
+        }
+        if (bulk_ok) {
+            issued_orient = copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid,
+                                                       kRestageFirst / 32, kRestageThreads / 32);
+        } else {
+            copy_out_tile<TH, TW, kRestageThreads>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid - kRestageFirst);
         }
     }
 
