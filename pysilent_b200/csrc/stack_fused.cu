@@ -221,6 +221,8 @@ struct TileA {
     static constexpr int X_PITCH = round_pitch(kPX * (A_RUNS - 1) + 10 > TW + 4 ? kPX * (A_RUNS - 1) + 10 : TW + 4);
     static constexpr int A_PITCH = round_pitch(kPX * A_RUNS > kPX * (B_RUNS - 1) + 10 ? kPX * A_RUNS : kPX * (B_RUNS - 1) + 10);
     static constexpr int X_PLANE = X_ROWS * X_PITCH, A_PLANE = A_ROWS * A_PITCH;
+    static constexpr int O_PITCH = round_pitch(TW);   // staged output rows (overlaid on the x planes)
+    static_assert(TH * O_PITCH <= 3 * X_PLANE, "output staging must fit in the x planes");
     static constexpr size_t kSmemBytes = (size_t)(3 * X_PLANE + 3 * A_PLANE) * sizeof(f2);
     static_assert(TW % kPX == 0 && TW % 4 == 0, "tile width must be a multiple of the run length");
 };
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
     __shared__ __align__(8) uint64_t tma_bar;
     f2 *sX = reinterpret_cast<f2 *>(smem_raw);   // [3][X_ROWS][X_PITCH]
     f2 *sA = sX + 3 * T::X_PLANE;                // [3][A_ROWS][A_PITCH]
+    f2 *sOut = sX;                               // [TH][O_PITCH] channel sums of the tile, valid after the S1 barrier
 
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
@@ -339,39 +342,87 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
     __syncthreads();
 
     // ---- S1: a = relu(conv3x3(x, rgc))   rows -1..TH, runs of 8 columns from -1               filters/rgc.py:13-16
-    for (int t = tid; t < T::A_ROWS * T::A_RUNS; t += NT) {
-        const int r = t % T::A_ROWS, k = t / T::A_ROWS;
-        const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kPX * k;
-        f2 acc[kPX][3];
+    if constexpr (S1_DEPTHWISE) {
+        // depthwise weights (midget_rgc): a task is ONE channel of THREE output rows x 8 columns. Its five input rows are
+        // loaded once (25 LDS.128 for 216 FFMA2, against 45 for a one-row three-channel task: this kernel is bound by
+        // shared-memory bandwidth). Input rows are visited in ascending order, so every output still sees its taps in
+        // the canonical (ky, kx) order.
+        static_assert(T::A_ROWS % 3 == 0, "S1 row triples");
+        constexpr int TRIPLES = T::A_ROWS / 3;
+        for (int t = tid; t < 3 * TRIPLES * T::A_RUNS; t += NT) {
+            const int rt = t % TRIPLES, rest = t / TRIPLES;
+            const int k = rest % T::A_RUNS, c = rest / T::A_RUNS;
+            const int r0 = 3 * rt, gx0 = tx0 - 1 + kPX * k;
+            f2 wt[9];
 #pragma unroll
-        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
-        if (gy >= 0 && gy < h) {
+            for (int tap = 0; tap < 9; ++tap) wt[tap] = P.w1[tap][c][c];
+            f2 acc[3][kPX];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int j = 0; j < 3; ++j)
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    f2 v[10];
-                    load_cols<5>(sX + ci * T::X_PLANE + (r + ky) * T::X_PITCH + kPX * k, v);
+                for (int p = 0; p < kPX; ++p) acc[j][p] = zero2();
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                f2 v[10];
+                load_cols<5>(sX + c * T::X_PLANE + (r0 + i) * T::X_PITCH + kPX * k, v);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int j = i - ky;
+                    if (j < 0 || j > 2) continue;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int p = 0; p < kPX; ++p)
-#pragma unroll
-                            for (int co = 0; co < 3; ++co)
-                                if (!S1_DEPTHWISE || ci == co)
-                                    acc[p][co] = fma2(P.w1[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                        for (int p = 0; p < kPX; ++p) acc[j][p] = fma2(wt[ky * 3 + kx], v[p + kx], acc[j][p]);
                 }
             }
-        }
 #pragma unroll
-        for (int co = 0; co < 3; ++co) {
-            f2 out[kPX];
+            for (int j = 0; j < 3; ++j) {
+                const int gy = ty0 - 1 + r0 + j;
+                const bool row_ok = gy >= 0 && gy < h;
+                f2 out[kPX];
 #pragma unroll
-            for (int p = 0; p < kPX; ++p) {
-                const int gx = gx0 + p;
-                out[p] = (gx >= 0 && gx < w) ? relu2_finite(acc[p][co]) : zero2();   // SAME padding of the next conv
+                for (int p = 0; p < kPX; ++p) {
+                    const int gx = gx0 + p;
+                    out[p] = (row_ok && gx >= 0 && gx < w) ? relu2_finite(acc[j][p]) : zero2();   // SAME padding of S2
+                }
+                store_cols8(sA + c * T::A_PLANE + (r0 + j) * T::A_PITCH + kPX * k, out);
             }
-            store_cols8(sA + co * T::A_PLANE + r * T::A_PITCH + kPX * k, out);
+        }
+    } else {
+    for (int t = tid; t < T::A_ROWS * T::A_RUNS; t += NT) {
+            const int r = t % T::A_ROWS, k = t / T::A_ROWS;
+            const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kPX * k;
+            f2 acc[kPX][3];
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+            if (gy >= 0 && gy < h) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        f2 v[10];
+                        load_cols<5>(sX + ci * T::X_PLANE + (r + ky) * T::X_PITCH + kPX * k, v);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                                for (int co = 0; co < 3; ++co)
+                                    if (!S1_DEPTHWISE || ci == co)
+                                        acc[p][co] = fma2(P.w1[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                f2 out[kPX];
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) {
+                    const int gx = gx0 + p;
+                    out[p] = (gx >= 0 && gx < w) ? relu2_finite(acc[p][co]) : zero2();   // SAME padding of the next conv
+                }
+                store_cols8(sA + co * T::A_PLANE + r * T::A_PITCH + kPX * k, out);
+            }
         }
     }
     __syncthreads();
@@ -404,14 +455,21 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
 #pragma unroll
         for (int p = 0; p < kPX; ++p)
             s[p] = add2(add2(relu2_finite(acc[p][0]), relu2_finite(acc[p][1])), relu2_finite(acc[p][2]));
-        // rows of bsum2 are w + 2 wide: pixel x lives in column x + 1 between two zero columns, so that stack_b's tile
-        // origin (x - 5) is an even column = a 16-byte aligned TMA box start
-        f2 *dst = bsum2 + ((size_t)pair * h + gy) * (w + 2) + gx0 + 1;
-#pragma unroll
-        for (int p = 0; p < kPX; ++p)
-            if (gx0 + p < w) dst[p] = s[p];
-        if (gx0 == 0) dst[-1] = zero2();
-        if (gx0 + kPX >= w) dst[w - gx0] = zero2();
+        // staged in shared memory (over the x planes, dead since S1) and written out row-contiguously below: a run is
+        // 64 B of ONE row, so storing it from here would touch 32 different rows per instruction
+        store_cols8(sOut + r * T::O_PITCH + kPX * k, s);
+    }
+    __syncthreads();
+    // rows of bsum2 are w + 2 wide: pixel x lives in column x + 1 between two zero columns, so that stack_b's tile
+    // origin (x - 5) is an even column = a 16-byte aligned TMA box start (and these stores are 8-byte, not 16-byte)
+    const int cols = min(TW, w - tx0);
+    for (int i = tid; i < TH * TW; i += NT) {
+        const int r = i / TW, x = i - r * TW, gy = ty0 + r;
+        if (gy >= h || x >= cols) continue;
+        f2 *dst = bsum2 + ((size_t)pair * h + gy) * (w + 2) + tx0 + 1 + x;
+        *dst = sOut[r * T::O_PITCH + x];
+        if (tx0 + x == 0) dst[-1] = zero2();
+        if (tx0 + x == w - 1) dst[1] = zero2();
     }
 }
 
