@@ -505,6 +505,7 @@ struct TileB {
     // an odd multiple of 16 B: the run-per-lane 128-bit stores AND the linear copy-out loads are conflict-free.
     static constexpr int ST_PITCH = TW * 3 + 4;                       // floats per staged row
     static constexpr int STAGE_F2 = 2 * TH * ST_PITCH / 2;            // float2 slots
+    static constexpr int G_PITCH = TW + 4;                            // floats per staged gray row (odd multiple of 16 B)
     static constexpr int FRONT_F2 = B_PLANE + CS_PLANE > STAGE_F2 ? B_PLANE + CS_PLANE : STAGE_F2;
     static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE) * sizeof(f2) + 64;
     static_assert(TW % kPX == 0, "tile width must be a multiple of the run length");
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
     float *sStage = reinterpret_cast<float *>(sB);   // [2][TH][ST_PITCH] NHWC staging, valid after the S4 barrier
     int *sWin = reinterpret_cast<int *>(sCD + 3 * T::CD_PLANE);   // [2 images][4 windows]
+    float *sGray = reinterpret_cast<float *>(sCD);                // [2][TH][G_PITCH] gray staging, valid after the S5 barrier
 
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
@@ -751,10 +753,10 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
         }
     }
     // the staging buffer is free again once the orient rows have been read out
-    if (orient) {
-        if (issued_orient) bulk_wait_read();
-        __syncthreads();
-    }
+    // every S5 warp is done reading the CD planes (the gray staging below overwrites them), and the orient rows have left
+    // the staging buffer
+    if (issued_orient) bulk_wait_read();
+    __syncthreads();
     int best0 = 0, best1 = 0;
     if (active) {
         const bool row_in = gy >= border && gy < h - border;
@@ -781,24 +783,23 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
 #pragma unroll
         for (int p = 0; p < kPX; ++p)
             g[p] = mul2(add2(add2(acc[p][0], acc[p][1]), acc[p][2]), make_float2(third, third));
-        const bool full = gx0 + kPX <= w;
-        const bool vec_ok = full && (w % 4) == 0;
         const size_t pix_a = ((size_t)img0 * h + gy) * w + gx0, pix_b = ((size_t)img1 * h + gy) * w + gx0;
         // stage padded_line_end in NHWC order: 96 contiguous bytes per image and run; written out row by row below
         store_nhwc8<0>(sStage + (size_t)r5 * T::ST_PITCH + 3 * kPX * k5, acc, true, kPX);
         store_nhwc8<1>(sStage + (size_t)(TH + r5) * T::ST_PITCH + 3 * kPX * k5, acc, true, kPX);
+        if (gray) {
+            if (bulk_ok) {   // staged over the (now dead) CD planes: rows of TW floats, written by bulk stores below
+                float4 *ga = reinterpret_cast<float4 *>(sGray + (size_t)r5 * T::G_PITCH + kPX * k5);
+                float4 *gb = reinterpret_cast<float4 *>(sGray + (size_t)(TH + r5) * T::G_PITCH + kPX * k5);
+                ga[0] = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+                ga[1] = make_float4(g[4].x, g[5].x, g[6].x, g[7].x);
+                gb[0] = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
+                gb[1] = make_float4(g[4].y, g[5].y, g[6].y, g[7].y);
+            } else {
 #pragma unroll
-        for (int lane = 0; lane < 2; ++lane) {
-            if (lane == 1 && !has_b) break;
-            const size_t pix = lane ? pix_b : pix_a;
-            if (gray) {
-                float *dst = gray + pix;
-                if (vec_ok) {
-                    reinterpret_cast<float4 *>(dst)[0] = lane ? make_float4(g[0].y, g[1].y, g[2].y, g[3].y)
-                                                              : make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
-                    reinterpret_cast<float4 *>(dst)[1] = lane ? make_float4(g[4].y, g[5].y, g[6].y, g[7].y)
-                                                              : make_float4(g[4].x, g[5].x, g[6].x, g[7].x);
-                } else {
+                for (int lane = 0; lane < 2; ++lane) {
+                    if (lane == 1 && !has_b) break;
+                    float *dst = gray + (lane ? pix_b : pix_a);
 #pragma unroll
                     for (int p = 0; p < kPX; ++p)
                         if (gx0 + p < w) dst[p] = lane ? g[p].y : g[p].x;
@@ -836,9 +837,23 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     // ---- copy-out: staged rows -> global NHWC, one bulk store per row ---------------------------------------------------
     fence_async_smem();
     __syncthreads();
+    if (gray && bulk_ok) {   // 2 * TH rows of TW floats, dealt like the line_end rows
+        const int per_warp = (2 * TH + NT / 32 - 1) / (NT / 32);
+        const int row = (tid >> 5) * per_warp + (tid & 31);
+        if ((tid & 31) < per_warp) {
+            if (row < 2 * TH) {
+                const int lane = row / TH, r = row - lane * TH, gyy = ty0 + r;
+                if (gyy < h && (lane == 0 || has_b))
+                    bulk_store(gray + ((size_t)(lane ? img1 : img0) * h + gyy) * w + tx0, sGray + (size_t)row * T::G_PITCH,
+                               (uint32_t)(min(TW, w - tx0) * sizeof(float)));
+            }
+            bulk_commit();
+            issued_line_end = true;
+        }
+    }
     if (line_end) {
         if (bulk_ok) {
-            issued_line_end = copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid, 0, NT / 32);
+            issued_line_end |= copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid, 0, NT / 32);
         } else {
             copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
         }
