@@ -233,10 +233,12 @@ __global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __g
 
     // ---- phase H: chain over the 6 x-taps. A thread owns one (output column, channel) and walks all rows of the tile:
     //      its six column-sum offsets and weights are set up once, each row then costs 6 LDS.64 + 6 FFMA2 + 1 store.
-    //      (192 of the 256 threads work here; consecutive lanes = consecutive columns, so the stores are coalesced.)
-    const int c = tid / kPairTileW;
-    const int ox = bx * kPairTileW + (tid % kPairTileW);
-    if (c >= 3 || ox >= w) return;
+    //      (192 of the 256 threads work here.)
+    // Lanes interleave (column, channel): three consecutive lanes read three consecutive column sums (the B, G, R bytes
+    // of one source pixel), so a warp's gather touches a third of the 128-byte lines it would with one channel per warp.
+    const int c = tid % 3;
+    const int ox = bx * kPairTileW + tid / 3;
+    if (tid >= 3 * kPairTileW || ox >= w) return;
     const int32_t *tx = idx_x + (size_t)ox * kTaps;
     const bool col_ok = __ldg(tx) >= 0;
     int off[kTaps];
