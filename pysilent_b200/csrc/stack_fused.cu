@@ -957,9 +957,9 @@ struct ThreadsA {
     static constexpr int value = (TileA<kTileHA, TW>::A_ROWS * TileA<kTileHA, TW>::A_RUNS + 31) / 32 * 32;
 };
 // threads of stack_b: one warp-rounded round of its widest phase (S3), which also covers one S5 task per thread
-template <int TW>
+template <int TH, int TW>
 struct ThreadsB {
-    static constexpr int value = ((kTileHB + 8) * TileB<kTileHB, TW>::C_RUNS + 31) / 32 * 32;
+    static constexpr int value = ((TH + 8) * TileB<TH, TW>::C_RUNS + 31) / 32 * 32;
 };
 
 template <int TW, bool DW, bool RGBY, bool PAIRED>
@@ -988,14 +988,31 @@ static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, cons
     return launch_a<TW, false, false, PAIRED>(in, P, tmap, bsum2, pairs, stream);
 }
 
+template <int TH, int TW>
+static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float *line_end, float *gray, int *winmax,
+                    cudaStream_t stream)
+{
+    const int h = S.b.h, w = S.b.w;
+    CUtensorMap map_b;
+    std::memset(&map_b, 0, sizeof(map_b));
+    using TB = TileB<TH, TW>;
+    constexpr int NT = ThreadsB<TH, TW>::value;
+    auto kern = stack_b_kernel<TH, TW, NT>;
+    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
+    S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
+    const dim3 grid(ceil_div(w, TW), ceil_div(h, TH), pairs);
+    kern<<<grid, NT, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
+    SILENT_LAUNCH_CHECK("stack_b_kernel");
+    return SILENT_OK;
+}
+
 template <int TW>
 static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int pairs, f2 *bsum2, float *orient,
                         float *line_end, float *gray, int *winmax, cudaStream_t stream, cudaEvent_t between_kernels)
 {
     const int h = S.a.h, w = S.a.w;
-    CUtensorMap map_x, map_b;
+    CUtensorMap map_x;
     std::memset(&map_x, 0, sizeof(map_x));
-    std::memset(&map_b, 0, sizeof(map_b));
     using TA = TileA<kTileHA, TW>;
     S.a.prefetch_pairs = 8;   // ~ the image pairs whose tiles are resident on the chip at once
     S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
@@ -1003,15 +1020,7 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
                        : dispatch_a<TW, false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream);
     if (rc != SILENT_OK) return rc;
     if (between_kernels) SILENT_CUDA(cudaEventRecord(between_kernels, stream));   // stage timing hook
-    using TB = TileB<kTileHB, TW>;
-    constexpr int NT = ThreadsB<TW>::value;
-    auto kern = stack_b_kernel<kTileHB, TW, NT>;
-    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
-    S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
-    const dim3 grid(ceil_div(w, TW), ceil_div(h, kTileHB), pairs);
-    kern<<<grid, NT, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
-    SILENT_LAUNCH_CHECK("stack_b_kernel");
-    return SILENT_OK;
+    return launch_b<kTileHB, TW>(S, pairs, bsum2, orient, line_end, gray, winmax, stream);
 }
 
 // pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
