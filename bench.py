@@ -184,11 +184,14 @@ def run_ours(args, rank, local_rank, world):
     bufs = (torch.empty((n, h, w, 3), dtype=torch.float32, device=dev), torch.empty((n, h, w, 3), dtype=torch.float32,
             device=dev), torch.empty((cap, 4), dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev))
     gather_cap = 16 * n
+    # the path's only exchange: feature points to every rank over NCCL/NVLink, one all-gather per step on a side stream
+    # (it overlaps the next step's kernels; the final barrier + synchronize below waits for the last one)
+    gatherer = sdist.PointGather(gather_cap, L, dev) if world > 1 else None
 
     def step():
         pipe.run_frames(frames, out=bufs)
-        if world > 1:   # the path's only exchange: feature points to every rank over NCCL/NVLink
-            sdist.gather_points_padded(bufs[2], bufs[3], rank * B, L, gather_cap)
+        if gatherer is not None:
+            gatherer.submit(bufs[2], bufs[3], rank * B)
 
     def barrier():
         if world > 1:

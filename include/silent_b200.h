@@ -172,6 +172,15 @@ enum {
 int silent_pointwise(const float *x_dev, const float *y_dev, size_t count, int kind, float *out_dev,
                      silent_stream stream);
 
+/* ---- multi-GPU: the path's only exchange is the feature-point gather ------------------------------------- */
+
+/* Packs one rank's points for a single fixed-size all-gather: packed_dev [capacity + 1][4] int64 = the first
+ * min(*count_dev, capacity) rows of points_dev with level_offset added to column 0 (level ids in global frame order),
+ * zero rows up to capacity, and the row (count, 0, 0, 0) last. points_dev must hold >= capacity rows. No reference
+ * counterpart (the reference is single-device, recognition_testing.py:64). */
+int silent_pack_points(const int64_t *points_dev, const int64_t *count_dev, int64_t capacity, int64_t level_offset,
+                       int64_t *packed_dev, silent_stream stream);
+
 /* ---- fused path ---------------------------------------------------------------------------------------------------- */
 
 /* S1-S7 of LineEndDisplayer.compile (recognition_testing.py:69-77) fused into two kernels (cut at the one-channel

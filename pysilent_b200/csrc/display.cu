@@ -146,6 +146,27 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float *__restrict_
     out[i] = r;
 }
 
+// rows [0, capacity) = the rank's points with the level id rebased to the global frame order (rows beyond the count are
+// zeroed), row `capacity` = (count, 0, 0, 0): ONE buffer, so the exchange is a single all-gather
+__global__ void __launch_bounds__(256) pack_points_kernel(const long long *__restrict__ points,
+                                                          const long long *__restrict__ count, long long capacity,
+                                                          long long level_offset, long long *__restrict__ packed)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > capacity) return;
+    const long long n = *count < capacity ? *count : capacity;
+    longlong2 a = make_longlong2(0, 0), b = make_longlong2(0, 0);
+    if (i == capacity) {
+        a.x = *count;
+    } else if (i < n) {
+        a = reinterpret_cast<const longlong2 *>(points)[2 * i];
+        b = reinterpret_cast<const longlong2 *>(points)[2 * i + 1];
+        a.x += level_offset;
+    }
+    reinterpret_cast<longlong2 *>(packed)[2 * i] = a;
+    reinterpret_cast<longlong2 *>(packed)[2 * i + 1] = b;
+}
+
 static unsigned blocks_for(size_t count) { return (unsigned)((count + 255) / 256); }
 
 }  // namespace silent
@@ -204,6 +225,18 @@ int silent_get_boosting(const float *input_dev, float *energy_dev, int n, int h,
     boosting_update_kernel<<<blocks_for(count), 256, 0, s>>>(input_dev, scratch_dev, energy_dev, n, h, w, exhaustion_max,
                                                             excitation_max, recovery_mode, fired_dev);
     SILENT_LAUNCH_CHECK("boosting_update_kernel");
+    return SILENT_OK;
+}
+
+int silent_pack_points(const int64_t *points_dev, const int64_t *count_dev, int64_t capacity, int64_t level_offset,
+                       int64_t *packed_dev, silent_stream stream)
+{
+    if (!points_dev || !count_dev || !packed_dev) return fail(SILENT_E_INVAL, "silent_pack_points: null argument");
+    if (capacity <= 0) return fail(SILENT_E_INVAL, "silent_pack_points: capacity must be positive");
+    pack_points_kernel<<<blocks_for((size_t)capacity + 1), 256, 0, (cudaStream_t)stream>>>(
+        (const long long *)points_dev, (const long long *)count_dev, (long long)capacity, (long long)level_offset,
+        (long long *)packed_dev);
+    SILENT_LAUNCH_CHECK("pack_points_kernel");
     return SILENT_OK;
 }
 

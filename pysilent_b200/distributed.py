@@ -69,3 +69,58 @@ def gather_points(points, count=None, frame_offset=0, levels_per_frame=1, capaci
     host_counts = counts.tolist()
     parts = [everyone[r * cap: r * cap + min(int(host_counts[r]), cap)] for r in range(world)]
     return torch.cat(parts, dim=0), counts
+
+
+class PointGather:
+    """The steady-state form of the gather: ONE fixed-size all-gather per batch, issued on a side stream so that it
+    overlaps the next batch's kernels; double-buffered, no host sync, no allocation per step.
+
+    ``submit`` (called on the compute stream right after the pipeline call) packs the rank's points and count into the
+    slot's send buffer with one small kernel (``silent_pack_points``) and queues the collective behind it on the side
+    stream; ``result`` waits for a slot and returns ``(points [K_total, 4], counts [world])`` in global frame order.
+    CUDA tensors + NCCL only (the gloo/CPU form is :func:`gather_points`).
+    """
+
+    def __init__(self, capacity, levels_per_frame, device, group=None, depth=2):
+        from . import _lib, _ops
+        self._lib, self._ops = _lib, _ops
+        self.capacity, self.levels, self.group = int(capacity), int(levels_per_frame), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
+        self.side = torch.cuda.Stream(self.device)
+        rows = self.capacity + 1
+        self.send = [torch.zeros((rows, 4), dtype=torch.int64, device=self.device) for _ in range(depth)]
+        self.recv = [torch.zeros((self.world, rows, 4), dtype=torch.int64, device=self.device) for _ in range(depth)]
+        self.packed = [torch.cuda.Event() for _ in range(depth)]
+        self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.submitted = 0
+
+    def submit(self, points, count, frame_offset):
+        """points: int64 CUDA ``[>= capacity, 4]``, count: 1-element int64 CUDA tensor. Returns the slot index."""
+        k = self.submitted % len(self.send)
+        self.submitted += 1
+        cur = torch.cuda.current_stream(self.device)
+        if points.shape[0] < self.capacity:
+            raise ValueError("points buffer holds %d rows, the gather capacity is %d" % (points.shape[0], self.capacity))
+        cur.wait_event(self.done[k])      # the slot's previous collective has read the send buffer (no-op at first use)
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib().silent_pack_points(
+                self._ops.ptr(points), self._ops.ptr(count), self.capacity, int(frame_offset) * self.levels,
+                self._ops.ptr(self.send[k]), self._ops.stream_ptr()), "silent_pack_points")
+        self.packed[k].record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.packed[k])
+            if self.world == 1:
+                self.recv[k][0].copy_(self.send[k], non_blocking=True)
+            else:
+                dist.all_gather_into_tensor(self.recv[k].view(-1, 4), self.send[k], group=self.group)
+            self.done[k].record(self.side)
+        return k
+
+    def result(self, slot):
+        self.done[slot].synchronize()
+        recv = self.recv[slot]
+        counts = recv[:, self.capacity, 0].clone()
+        host = counts.tolist()
+        parts = [recv[r, :min(int(host[r]), self.capacity)] for r in range(self.world)]
+        return torch.cat(parts, dim=0), counts

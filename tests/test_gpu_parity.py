@@ -550,3 +550,62 @@ def test_displayer_callback_structure_and_state(c_oracle, default_filters):
     assert_bits(disp.energy_values, e1, "state re-initialised on shape change")
     shown = disp.display(small)
     assert len(shown) == 7 and float(np.nanmax(shown[6])) <= 1.0
+
+
+# ---- multi-GPU exchange: the feature-point gather -------------------------------------------------------------------------
+
+def test_point_gather_pack_and_single_rank_path():
+    """silent_pack_points + PointGather on one GPU (world 1): level ids rebased to global frame order, rows beyond the
+    count zeroed, count row last; repeated submits reuse the two slots."""
+    from pysilent_b200.distributed import PointGather
+    rs = np.random.RandomState(77)
+    cap, levels = 48, 6
+    g = PointGather(cap, levels, torch.device("cuda", 0))
+    for step, k_valid in enumerate((5, 0, 48, 60, 17)):
+        pts = torch.from_numpy(rs.randint(0, 190, size=(64, 4)).astype(np.int64)).cuda()
+        count = torch.tensor([k_valid], dtype=torch.int64, device="cuda")
+        slot = g.submit(pts, count, frame_offset=3 + step)
+        got, counts = g.result(slot)
+        keep = min(k_valid, cap)
+        want = pts[:keep].clone()
+        want[:, 0] += (3 + step) * levels
+        assert int(counts[0]) == k_valid and torch.equal(got, want)
+        send = g.send[slot].cpu().numpy()
+        assert (send[keep:cap] == 0).all() and send[cap, 0] == k_valid
+
+
+def _nccl_gather_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pysilent_b200 import LineEndPipeline
+    from pysilent_b200.distributed import PointGather, shard_range
+    frames = np.stack([synthetic_frame(1, i, 480, 640) for i in range(5)])
+    lo, hi = shard_range(len(frames), rank, world)
+    pipe = LineEndPipeline(zoom_ratio=1.3)
+    res = pipe.run_frames(torch.from_numpy(frames[lo:hi]).cuda())
+    L = res.orient.shape[0] // (hi - lo)
+    pts = torch.zeros((256, 4), dtype=torch.int64, device="cuda")
+    pts[: len(res.points)] = res.points
+    g = PointGather(256, L, torch.device("cuda", rank))
+    got = None
+    for _ in range(3):   # steady-state reuse of the slots
+        got, counts = g.result(g.submit(pts, torch.tensor([len(res.points)], device="cuda"), lo))
+    np.save(os.path.join(out, "nccl_%d.npy" % rank), got.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_point_gather_two_gpus_nccl(tmp_path):
+    """Frames sharded over 2 GPUs, points gathered over NCCL: equal to the single-GPU run of the whole batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    from pysilent_b200 import LineEndPipeline
+    mp.spawn(_nccl_gather_worker, args=(2, 29600 + os.getpid() % 300, str(tmp_path)), nprocs=2, join=True)
+    frames = np.stack([synthetic_frame(1, i, 480, 640) for i in range(5)])
+    want = LineEndPipeline(zoom_ratio=1.3).run_frames(torch.from_numpy(frames).cuda()).points.cpu().numpy()
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / ("nccl_%d.npy" % r)), want)
