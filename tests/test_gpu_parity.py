@@ -609,3 +609,42 @@ def test_point_gather_two_gpus_nccl(tmp_path):
     want = LineEndPipeline(zoom_ratio=1.3).run_frames(torch.from_numpy(frames).cuda()).points.cpu().numpy()
     for r in range(2):
         assert np.array_equal(np.load(tmp_path / ("nccl_%d.npy" % r)), want)
+
+
+def test_outputs_stay_inside_their_buffers():
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES of the bulk / staged stores are caught
+    with canaries: every output lives in one arena between guard bands that must come back untouched (full tiles, ragged
+    tiles, odd batch, a level width that is not a multiple of 4 = the non-bulk fallback)."""
+    from pysilent_b200 import LineEndPipeline
+    guard = 4096   # int64 words = 32 KB between tensors
+    for (shape, center, scale, batch) in (((300, 420), (96, 64), 2 ** .5, 3), ((240, 330), (50, 36), 1.4, 2),
+                                          ((1080, 1920), (288, 192), 2 ** .5, 5)):
+        frames = np.stack([synthetic_frame(9, i, *shape) for i in range(batch)])
+        pipe = LineEndPipeline(output_size=center, zoom_ratio=scale)
+        dev = torch.from_numpy(frames).cuda()
+        plan = pipe.plan_for(dev)
+        n = batch * plan.levels
+        elems = n * plan.h * plan.w * 3
+        words_t = (elems * 4 + 7) // 8
+        cap = 64 * n
+        arena = torch.full((5 * guard + 2 * words_t + cap * 4 + 1,), 0x5A5A5A5A5A5A5A5A, dtype=torch.int64, device="cuda")
+        off = guard
+        orient = arena[off: off + words_t].view(torch.float32)[:elems].view(n, plan.h, plan.w, 3)
+        off += words_t + guard
+        line_end = arena[off: off + words_t].view(torch.float32)[:elems].view(n, plan.h, plan.w, 3)
+        off += words_t + guard
+        points = arena[off: off + cap * 4].view(cap, 4)
+        off += cap * 4 + guard
+        count = arena[off: off + 1]
+        count.zero_()
+        used = torch.zeros_like(arena, dtype=torch.bool)
+        for t in (orient, line_end, points, count):
+            start = (t.data_ptr() - arena.data_ptr()) // 8
+            used[start: start + (t.numel() * t.element_size() + 7) // 8] = True
+        pipe.run_frames(dev, out=(orient, line_end, points, count))
+        torch.cuda.synchronize()
+        assert bool((arena[~used] == 0x5A5A5A5A5A5A5A5A).all()), "a kernel wrote outside its output tensors %s" % (shape,)
+        ref = pipe.run_frames(dev)
+        assert torch.equal(ref.orient.nan_to_num(-1.0), orient.nan_to_num(-1.0))
+        assert torch.equal(ref.padded_line_end.nan_to_num(-1.0), line_end.nan_to_num(-1.0))
+        assert torch.equal(ref.points, points[: int(count.item())])
