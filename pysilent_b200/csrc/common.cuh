@@ -37,6 +37,35 @@ constexpr int kMaxKernel = 7;
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch: the kernels of one pipeline step are launched with the stream-serialisation
+//      attribute, so a kernel's CTAs are scheduled while its predecessor drains and only its FIRST instruction waits for
+//      the predecessor's memory (no launch gap between the step's 7 kernels; matters most at batch 1). A kernel that is
+//      launched without the attribute passes both instructions at once.
+__device__ __forceinline__ void pdl_enter()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- canonical float32 element ops -----------------------------------------------------------------------------------
 
 __device__ __forceinline__ float canon_relu(float v) { return v < 0.0f ? 0.0f : v; }   // NaN propagates

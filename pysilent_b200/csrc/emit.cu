@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict
 __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
                                                          const float *__restrict__ pooled, int *__restrict__ row_count)
 {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict
 // One CTA per level: exclusive scan of the level's row counts -> row_offset (within the level, in place) + level_total.
 __global__ void __launch_bounds__(256) scan_level_kernel(int *__restrict__ row_count, int h, int *__restrict__ level_total)
 {
+    pdl_enter();
     __shared__ int s_warp[8];
     __shared__ int s_carry;
     int *rows = row_count + (size_t)blockIdx.x * h;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict
                                                          const long long *__restrict__ level_offset,
                                                          long long *__restrict__ points, long long capacity)
 {
+    pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -159,6 +162,7 @@ __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict
 __global__ void __launch_bounds__(1024) scan_rows_kernel(const int *__restrict__ row_count, int rows,
                                                          long long *__restrict__ row_offset, long long *__restrict__ total)
 {
+    pdl_enter();
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -300,15 +304,18 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     }
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
     const unsigned blocks = (unsigned)ceil_div(rows, 8);
-    count_rows_kernel<<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_offset);
+    SILENT_CUDA(launch_dependent(count_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
+                                 (const float *)pooled, row_offset));
     SILENT_LAUNCH_CHECK("count_rows_kernel");
-    scan_level_kernel<<<n, 256, 0, stream>>>(row_offset, h, level_total);
+    SILENT_CUDA(launch_dependent(scan_level_kernel, dim3(n), dim3(256), 0, stream, row_offset, h, level_total));
     SILENT_LAUNCH_CHECK("scan_level_kernel");
-    scan_rows_kernel<<<1, 1024, 0, stream>>>(level_total, n, level_offset, (long long *)count);
+    SILENT_CUDA(launch_dependent(scan_rows_kernel, dim3(1), dim3(1024), 0, stream, (const int *)level_total, n, level_offset,
+                                 (long long *)count));
     SILENT_LAUNCH_CHECK("scan_rows_kernel");
     if (capacity > 0) {
-        write_rows_kernel<<<blocks, 256, 0, stream>>>(value, rows, h, w, g, pooled, row_offset, level_offset,
-                                                      (long long *)points, (long long)capacity);
+        SILENT_CUDA(launch_dependent(write_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
+                                     (const float *)pooled, (const int *)row_offset, (const long long *)level_offset,
+                                     (long long *)points, (long long)capacity));
         SILENT_LAUNCH_CHECK("write_rows_kernel");
     }
     return SILENT_OK;

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __g
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     f2 *sV = reinterpret_cast<f2 *>(smem_raw);                          // [th][vpitch] column sums (frame A, frame B)
+    pdl_enter();
 
     const int tid = threadIdx.x;
     int k = 0;
@@ -309,7 +310,7 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
         smem = std::max(smem, (size_t)pl.th * pl.vpitch * sizeof(f2) + (size_t)pl.th * kTaps * 8);
     }
     P.tile_start[plan->levels] = tiles;
-    pyramid_pair_kernel<<<dim3(tiles, pairs), kPairThreads, smem, stream>>>(P);
+    SILENT_CUDA(launch_dependent(pyramid_pair_kernel, dim3(tiles, pairs), dim3(kPairThreads), smem, stream, P));
     SILENT_LAUNCH_CHECK("pyramid_pair_kernel");
     return SILENT_OK;
 }

@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
     using T = TileA<TH, TW>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
+    pdl_enter();
     f2 *sX = reinterpret_cast<f2 *>(smem_raw);   // [3][X_ROWS][X_PITCH]
     f2 *sA = sX + 3 * T::X_PLANE;                // [3][A_ROWS][A_PITCH]
     f2 *sOut = sX;                               // [TH][O_PITCH] channel sums of the tile, valid after the S1 barrier
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     using T = TileB<TH, TW>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
+    pdl_enter();
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
     f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
@@ -970,7 +972,7 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
     auto kern = stack_a_kernel<kTileHA, TW, kThreadsA, DW, RGBY, PAIRED>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
     const dim3 grid(ceil_div(P.w, TW), ceil_div(P.h, kTileHA), pairs);
-    kern<<<grid, kThreadsA, T::kSmemBytes, stream>>>(pyr, P, tmap, bsum2);
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(kThreadsA), T::kSmemBytes, stream, pyr, P, tmap, bsum2));
     SILENT_LAUNCH_CHECK("stack_a_kernel");
     return SILENT_OK;
 }
@@ -1001,7 +1003,8 @@ static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
     S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
     const dim3 grid(ceil_div(w, TW), ceil_div(h, TH), pairs);
-    kern<<<grid, NT, TB::kSmemBytes, stream>>>(bsum2, S.b, map_b, orient, line_end, gray, winmax);
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, orient, line_end, gray,
+                                 winmax));
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
