@@ -463,14 +463,21 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
     __syncthreads();
     // rows of bsum2 are w + 2 wide: pixel x lives in column x + 1 between two zero columns, so that stack_b's tile
     // origin (x - 5) is an even column = a 16-byte aligned TMA box start (and these stores are 8-byte, not 16-byte)
-    const int cols = min(TW, w - tx0);
-    for (int i = tid; i < TH * TW; i += NT) {
-        const int r = i / TW, x = i - r * TW, gy = ty0 + r;
-        if (gy >= h || x >= cols) continue;
-        f2 *dst = bsum2 + ((size_t)pair * h + gy) * (w + 2) + tx0 + 1 + x;
-        *dst = sOut[r * T::O_PITCH + x];
-        if (tx0 + x == 0) dst[-1] = zero2();
-        if (tx0 + x == w - 1) dst[1] = zero2();
+    constexpr int ROWS_PER_PASS = NT / TW;   // a thread keeps its column and steps down the rows: no index arithmetic
+    static_assert(ROWS_PER_PASS >= 1, "stack_a needs at least TW threads");
+    const int x = tid % TW, r0 = tid / TW;
+    if (r0 < ROWS_PER_PASS && tx0 + x < w) {
+        const bool first = tx0 + x == 0, last = tx0 + x == w - 1;
+        const int rows = min(TH, h - ty0);
+        f2 *dst = bsum2 + ((size_t)pair * h + ty0 + r0) * (w + 2) + tx0 + 1 + x;
+        const f2 *src = sOut + r0 * T::O_PITCH + x;
+        for (int r = r0; r < rows; r += ROWS_PER_PASS) {
+            *dst = *src;
+            if (first) dst[-1] = zero2();
+            if (last) dst[1] = zero2();
+            dst += (size_t)ROWS_PER_PASS * (w + 2);
+            src += ROWS_PER_PASS * T::O_PITCH;
+        }
     }
 }
 
