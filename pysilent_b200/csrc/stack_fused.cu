@@ -381,10 +381,15 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
                 const int gy = ty0 - 1 + r0 + j;
                 const bool row_ok = gy >= 0 && gy < h;
                 f2 out[kPX];
+                if (row_ok && gx0 >= 0 && gx0 + kPX <= w) {   // the common case: the whole run lies inside the level
 #pragma unroll
-                for (int p = 0; p < kPX; ++p) {
-                    const int gx = gx0 + p;
-                    out[p] = (row_ok && gx >= 0 && gx < w) ? relu2_finite(acc[j][p]) : zero2();   // SAME padding of S2
+                    for (int p = 0; p < kPX; ++p) out[p] = relu2_finite(acc[j][p]);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p) {
+                        const int gx = gx0 + p;
+                        out[p] = (row_ok && gx >= 0 && gx < w) ? relu2_finite(acc[j][p]) : zero2();   // SAME padding of S2
+                    }
                 }
                 store_cols8(sA + c * T::A_PLANE + (r0 + j) * T::A_PITCH + kPX * k, out);
             }
@@ -608,13 +613,22 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             }
         }
         f2 cs[kPX];
+        if (gx0 >= 0 && gx0 + kPX <= w) {   // the common case: the whole run lies inside the level
 #pragma unroll
-        for (int p = 0; p < kPX; ++p) {
-            const int gx = gx0 + p;
-            const bool inside = gx >= 0 && gx < w;
+            for (int p = 0; p < kPX; ++p) {
 #pragma unroll
-            for (int co = 0; co < 3; ++co) acc[p][co] = inside ? relu2_finite(acc[p][co]) : zero2();
-            cs[p] = add2(add2(acc[p][0], acc[p][1]), acc[p][2]);
+                for (int co = 0; co < 3; ++co) acc[p][co] = relu2_finite(acc[p][co]);
+                cs[p] = add2(add2(acc[p][0], acc[p][1]), acc[p][2]);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) {
+                const int gx = gx0 + p;
+                const bool inside = gx >= 0 && gx < w;
+#pragma unroll
+                for (int co = 0; co < 3; ++co) acc[p][co] = inside ? relu2_finite(acc[p][co]) : zero2();
+                cs[p] = add2(add2(acc[p][0], acc[p][1]), acc[p][2]);
+            }
         }
         store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
         const int rd = r - 3;   // row in the CD planes (origin -1)
@@ -689,10 +703,15 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
                     c[2 * q + 1] = make_float2(tq.z, tq.w);
                 }
             }
+            if (gx0 >= 0 && gx0 + kPX <= w) {   // (rows outside the level never get here)
 #pragma unroll
-            for (int p = 0; p < kPX; ++p) {
-                const int gx = gx0 + p;
-                c[p] = (row_ok && gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
+                for (int p = 0; p < kPX; ++p) c[p] = mul2(c[p], gain[p]);
+            } else {
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) {
+                    const int gx = gx0 + p;
+                    c[p] = (row_ok && gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
+                }
             }
             store_cols8(cd, c);
         }
