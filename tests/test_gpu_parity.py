@@ -648,3 +648,21 @@ def test_outputs_stay_inside_their_buffers():
         assert torch.equal(ref.orient.nan_to_num(-1.0), orient.nan_to_num(-1.0))
         assert torch.equal(ref.padded_line_end.nan_to_num(-1.0), line_end.nan_to_num(-1.0))
         assert torch.equal(ref.points, points[: int(count.item())])
+
+
+def test_pipeline_four_channel_frames(c_oracle, default_filters):
+    """BGRA frames (4 interleaved bytes per pixel, 3 colours used): the frame-pair pyramid kernel strides by the frame's
+    channel count; equal to the 3-channel run of the same pixels and to the oracle."""
+    from pysilent_b200 import LineEndPipeline
+    bgr = np.stack([synthetic_frame(6, i, 360, 480) for i in range(3)])
+    bgra = np.concatenate([bgr, np.full(bgr.shape[:3] + (1,), 255, np.uint8)], axis=-1)
+    pipe = LineEndPipeline(output_size=(96, 64), zoom_ratio=1.5)
+    want = pipe.run_frames(torch.from_numpy(bgr).cuda())
+    got = pipe.run_frames(torch.from_numpy(bgra).cuda())
+    assert torch.equal(got.orient.nan_to_num(-1.0), want.orient.nan_to_num(-1.0))
+    assert torch.equal(got.padded_line_end.nan_to_num(-1.0), want.padded_line_end.nan_to_num(-1.0))
+    assert torch.equal(got.points, want.points)
+    pyr, ref = _oracle_pipeline(c_oracle, bgr, (96, 64), 1.5, default_filters)
+    _check_stack(got, ref, None, "BGRA frames")
+    host = pipe.run_host(bgra)
+    assert np.array_equal(host.orient, ref["orient"], equal_nan=True) and np.array_equal(host.points, ref["points"])
