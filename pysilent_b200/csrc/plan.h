@@ -14,7 +14,8 @@ struct LevelInfo {
 
 // Launch geometry of pyramid_pair_kernel for one level: x tiles of kPairTileW output columns; per tile the span of
 // aligned 32-bit words of a frame row that its x-taps touch.
-constexpr int kPairTileW = 64, kPairMaxTiles = 64, kPairMaxLevels = 16;
+constexpr int kPairTileWMax = 85;   // phase H runs one thread per (column, channel): 3 * 85 <= 256 threads
+constexpr int kPairMaxTiles = 64, kPairMaxLevels = 16;
 struct PairLevel {
     int ntx = 0, th = 0, vpitch = 0;
     int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];
@@ -60,6 +61,7 @@ struct silent_plan {
     std::vector<float> w_y, w_x;
     std::vector<silent::PairLevel> pair;   // per level
     bool pair_ok = false;
+    int pair_tile_w = 64;                  // output columns per tile of the frame-pair pyramid kernel (see plan.cu)
     int *d_pair_words = nullptr;           // [L][kPairMaxTiles][2]: (word_lo, nwords) per level and x tile
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;

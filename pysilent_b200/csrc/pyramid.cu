@@ -134,7 +134,7 @@ struct PairParams {
     const float *w_y, *w_x;
     const int *words;               // [L][kPairMaxTiles][2]: first 32-bit word of a frame row and word count per x tile
     int H, row_bytes, FC;           // frame rows, bytes per frame row, interleaved channels
-    int h, w, L, B, ntx;
+    int h, w, L, B, ntx, tile_w;
     // ONE launch covers every level: blockIdx.x enumerates the tiles of a frame pair with the COARSEST level first (it
     // pulls the whole frame through L2; the finer levels, whose crops are subsets, then hit L2), blockIdx.y the pair.
     int th[kPairMaxLevels];           // output rows per tile
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __g
     // Lanes interleave (column, channel): three consecutive lanes read three consecutive column sums (the B, G, R bytes
     // of one source pixel), so a warp's gather touches a third of the 128-byte lines it would with one channel per warp.
     const int c = tid % 3;
-    const int ox = bx * kPairTileW + tid / 3;
-    if (tid >= 3 * kPairTileW || ox >= w) return;
+    const int ox = bx * P.tile_w + tid / 3;
+    if (tid >= 3 * P.tile_w || ox >= w) return;
     const int32_t *tx = idx_x + (size_t)ox * kTaps;
     const bool col_ok = __ldg(tx) >= 0;
     int off[kTaps];
@@ -298,6 +298,7 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     P.FC = p.frame_c;
     P.h = plan->h, P.w = plan->w, P.L = plan->levels, P.B = batch;
     P.ntx = plan->pair[0].ntx;
+    P.tile_w = plan->pair_tile_w;
     size_t smem = 0;
     int tiles = 0;
     for (int k = 0; k < plan->levels; ++k) {   // coarsest level first
