@@ -11,7 +11,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",                      # canonical order: every FMA in the library is an explicit fmaf()
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v",
-]
+] + (["-DSILENT_PAIR_THREADS=" + os.environ["SILENT_PAIR_THREADS"]] if os.environ.get("SILENT_PAIR_THREADS") else [])
 
 
 def _nvcc():

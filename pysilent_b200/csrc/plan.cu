@@ -197,14 +197,14 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
         }
         pl.vpitch = (widest / 4) * 18;   // 16 byte-columns + 2 padding slots per 128-bit group (pyramid.cu: kVGroup)
         // rows per tile: fit the column-sum buffer in ~72 KB (3 CTAs per SM) and make the phase-V task count
-        // (rows x 128-bit groups) fill whole rounds of the 256 threads -- a 1.09-round tile idles the CTA at the barrier
+        // (rows x 128-bit groups) fill whole rounds of the CTA's threads -- a 1.09-round tile idles the CTA at the barrier
         const int groups = widest / 4;
         double best = -1.0;
         pl.th = 1;
         for (int th = 1; th <= 48; ++th) {   // (16 was measured 3 % slower: taller tiles amortise the per-tile set-up)
             if ((size_t)th * pl.vpitch * 8 > 72 * 1024 && th > 1) break;
-            const int tasks = th * groups, rounds = ceil_div(tasks, 256);
-            const double fill = (double)tasks / (256.0 * rounds) + 0.002 * th;   // prefer taller tiles on ties
+            const int tasks = th * groups, rounds = ceil_div(tasks, kPairThreads);
+            const double fill = (double)tasks / ((double)kPairThreads * rounds) + 0.002 * th;   // prefer taller tiles on ties
             if (fill > best) best = fill, pl.th = th;
         }
         if ((size_t)pl.th * pl.vpitch * 8 > 190 * 1024) plan->pair_ok = false;

@@ -16,6 +16,10 @@ struct LevelInfo {
 // aligned 32-bit words of a frame row that its x-taps touch.
 constexpr int kPairTileWMax = 85;   // phase H runs one thread per (column, channel): 3 * 85 <= 256 threads
 constexpr int kPairMaxTiles = 64, kPairMaxLevels = 16;
+#ifndef SILENT_PAIR_THREADS
+#define SILENT_PAIR_THREADS 256
+#endif
+constexpr int kPairThreads = SILENT_PAIR_THREADS;   // threads per CTA of pyramid_pair_kernel
 struct PairLevel {
     int ntx = 0, th = 0, vpitch = 0;
     int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];

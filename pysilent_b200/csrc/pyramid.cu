@@ -124,7 +124,6 @@ int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, fl
 // ---------------------------------------------------------------------------------------------------------------------
 
 typedef float2 f2;
-constexpr int kPairThreads = 256;
 constexpr int kVGroup = 18;   // float2 slots per group of 16 byte-columns in the column-sum buffer (16 + 2 of padding)
 
 struct PairParams {
