@@ -8,12 +8,15 @@
 //  * pyramid_kernel      one thread per output pixel, NHWC float32 output: the stand-alone from_image operator, any
 //                        channel count / frame dtype.
 //  * pyramid_pair_kernel the pipeline's producer. One CTA = one tile of one level for TWO frames in lockstep (float2
-//                        lanes, like the stack kernels). Phase V walks ALIGNED 32-bit words of the uint8 frame down the
-//                        6 tap rows (coalesced, 4 byte-columns per load), converts with PRMT + FADD2 (the I2F pipe is
+//                        lanes, like the stack kernels). Phase V walks ALIGNED 128-bit words of the uint8 frame down the
+//                        6 tap rows (coalesced, 16 byte-columns per load), converts with PRMT + FADD2 (the I2F pipe is
 //                        16/clk/SM on B200: measured 2.4x slower), accumulates with FFMA2 and parks the column sums in
 //                        shared memory; phase H gathers 6 of them per output sample. ~10x fewer instructions than the
 //                        per-pixel kernel (which re-converts every tap for every pixel). Output is the pair-interleaved
 //                        planar layout xpair[pair][c][y][x] = (frame A, frame B) that stack_a_kernel loads verbatim.
+//                        One launch covers every level, coarsest first (it pulls a frame pair through L2 once; finer
+//                        levels re-read their crops from L2) and bulk-prefetches the next pair's rows into L2. Tile
+//                        width (72 columns for 288-wide levels) and height are chosen per plan (plan.cu).
 #include <algorithm>
 
 #include "plan.h"

@@ -14,11 +14,16 @@
 //  * TWO KERNELS, CUT AT THE ONE-CHANNEL TENSOR. stack_a: x -> rgc -> rgby -> channel sum b (1 channel, written as
 //    interleaved pairs); stack_b: b -> stripe -> regulator -> end -> outputs. The stripe filter only needs the channel
 //    sum of b, so the cut costs 2 x 1/6 of the output traffic but shrinks halos (2 and 5 instead of 7), which keeps
-//    the redundant halo arithmetic at ~10 % with 32 x 64 tiles.
+//    the redundant halo arithmetic at ~15 % with 32 x 48 tiles (288-wide levels: 6 tiles, no ragged edge).
 //  * zero weights cost nothing: rgc is depthwise and rgby has 28 structural zeros; both patterns are verified on the
 //    host and compiled out (dense variants exist for arbitrary weights).
+//  * TILES IN BY TMA, ROWS OUT BY BULK STORES. Inputs arrive as one cp.async.bulk.tensor box (zero fill = SAME padding);
+//    outputs are staged in shared memory in NHWC order and leave as one cp.async.bulk store per row, issued by a few
+//    lanes of every warp; in stack_b the warps that have no S5 task restage and store `orient` behind a named barrier
+//    while the others run the end filter. Kernels of one step are chained by programmatic dependent launch.
 // Evaluation order = canonical order of oracle/silent_oracle.c (chains in (ky, ci, kx) order), so results are
-// bit-identical to it. HBM-bound by design; tensor cores do not apply (3-channel fp32 stencils).
+// bit-identical to it. Tensor cores do not apply (3-channel fp32 stencils); measured, the path is bound by packed-fp32
+// issue and shared-memory bandwidth rather than HBM.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -662,7 +667,6 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             for (int co = 0; co < 3; ++co) store_cols8(sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k, z);
             continue;
         }
-        const bool row_ok = true;
         f2 m[kPX];
 #pragma unroll
         for (int p = 0; p < kPX; ++p) m[p] = zero2();
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
 #pragma unroll
                 for (int p = 0; p < kPX; ++p) {
                     const int gx = gx0 + p;
-                    c[p] = (row_ok && gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
+                    c[p] = (gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
                 }
             }
             store_cols8(cd, c);
