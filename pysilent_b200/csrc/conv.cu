@@ -40,13 +40,29 @@ __global__ void __launch_bounds__(kConvTileW *kConvTileH)
     }
     __syncthreads();
 
-    int same = 1;
-    if (cin < 2) same = 0;
-    for (int i = tid; i < nw && same; i += nthreads) {
+    // Filter structure, decided by the whole CTA: "uniform-in" = every input-channel slice bitwise identical (stripe and
+    // blur banks), "uniform-out" = additionally every output channel of a tap identical (blur_tensor). Uniform-in chains
+    // run over the channel sum s = ((x0 + x1) + x2 ...), which is then staged ONCE per tile; with uniform-out all output
+    // channels share one chain (identical bits), so it is evaluated once: 49 instead of 3136 multiply-adds per pixel for
+    // the 8-channel regulator of config C4.
+    int same_in = cin >= 2, same_out = 1;
+    for (int i = tid; i < nw && (same_in || same_out); i += nthreads) {
         const int co = i % cout, t = i / (cin * cout);
-        if (__float_as_uint(s_w[i]) != __float_as_uint(s_w[t * cin * cout + co])) same = 0;
+        if (__float_as_uint(s_w[i]) != __float_as_uint(s_w[t * cin * cout + co])) same_in = 0;
+        if (__float_as_uint(s_w[i]) != __float_as_uint(s_w[t * cin * cout])) same_out = 0;
     }
-    const bool uniform_in = __syncthreads_and(same) != 0;
+    const bool uniform_in = __syncthreads_and(same_in) != 0;
+    const bool uniform_out = __syncthreads_and(same_out) != 0 && uniform_in;
+    float *s_sum = s_x + th * tw * cin;   // [th][tw] channel sums (uniform-in only)
+    if (uniform_in) {
+        for (int i = tid; i < th * tw; i += nthreads) {
+            const float *px = s_x + i * cin;
+            float v = px[0];
+            for (int ci = 1; ci < cin; ++ci) v = v + px[ci];
+            s_sum[i] = v;
+        }
+        __syncthreads();
+    }
 
     const int ox = blockIdx.x * kConvTileW + threadIdx.x, oy = blockIdx.y * kConvTileH + threadIdx.y;
     if (ox >= w || oy >= h) return;
@@ -56,25 +72,32 @@ __global__ void __launch_bounds__(kConvTileW *kConvTileH)
     for (int co = 0; co < kMaxChannels; ++co) acc[co] = 0.0f;
 
     // chain order (ky, ci, kx): one input row-channel at a time, as in the register-blocked fused kernels
-    for (int ky = 0; ky < k; ++ky) {
-        if (uniform_in) {
-            for (int kx = 0; kx < k; ++kx) {
-                const float *px = s_x + ((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin;
-                const float *pw = s_w + (ky * k + kx) * cin * cout;
-                float s = px[0];
-                for (int ci = 1; ci < cin; ++ci) s = s + px[ci];
+    if (uniform_out) {
+        float a = 0.0f;
+        for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx)
+                a = fmaf(s_w[(ky * k + kx) * cin * cout], s_sum[(threadIdx.y + ky) * tw + threadIdx.x + kx], a);
 #pragma unroll
-                for (int co = 0; co < kMaxChannels; ++co)
-                    if (co < cout) acc[co] = fmaf(pw[co], s, acc[co]);
-            }
-        } else {
-            for (int ci = 0; ci < cin; ++ci) {
+        for (int co = 0; co < kMaxChannels; ++co) acc[co] = a;
+    } else {
+        for (int ky = 0; ky < k; ++ky) {
+            if (uniform_in) {
                 for (int kx = 0; kx < k; ++kx) {
-                    const float v = s_x[((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin + ci];
-                    const float *pw = s_w + ((ky * k + kx) * cin + ci) * cout;
+                    const float sv = s_sum[(threadIdx.y + ky) * tw + threadIdx.x + kx];
+                    const float *pw = s_w + (ky * k + kx) * cin * cout;
 #pragma unroll
                     for (int co = 0; co < kMaxChannels; ++co)
-                        if (co < cout) acc[co] = fmaf(pw[co], v, acc[co]);
+                        if (co < cout) acc[co] = fmaf(pw[co], sv, acc[co]);
+                }
+            } else {
+                for (int ci = 0; ci < cin; ++ci) {
+                    for (int kx = 0; kx < k; ++kx) {
+                        const float v = s_x[((threadIdx.y + ky) * tw + threadIdx.x + kx) * cin + ci];
+                        const float *pw = s_w + ((ky * k + kx) * cin + ci) * cout;
+#pragma unroll
+                        for (int co = 0; co < kMaxChannels; ++co)
+                            if (co < cout) acc[co] = fmaf(pw[co], v, acc[co]);
+                    }
                 }
             }
         }
@@ -104,7 +127,7 @@ static int launch_conv(const float *x, int n, int h, int w, int cin, const float
     if (k < 1 || k > kMaxKernel || (k % 2) == 0)
         return fail(SILENT_E_SHAPE, "%s: filter size must be odd and <= %d (got %d)", who, kMaxKernel, k);
     if (n > 65535) return fail(SILENT_E_SHAPE, "%s: at most 65535 levels per call", who);
-    const size_t smem = ((size_t)k * k * cin * cout + (size_t)(kConvTileH + k - 1) * (kConvTileW + k - 1) * cin) * 4;
+    const size_t smem = ((size_t)k * k * cin * cout + (size_t)(kConvTileH + k - 1) * (kConvTileW + k - 1) * (cin + 1)) * 4;
     if (smem > 48 * 1024) {
         SILENT_CUDA(cudaFuncSetAttribute(conv2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
