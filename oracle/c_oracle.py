@@ -195,7 +195,11 @@ def line_end_stack(pyramid, weights, region_divisor=2.0):
     lib().so_line_end_stack(x, n, h, w, W["rgc"], W["rgby"], W["stripe"], W["blur"], W["blur"].shape[0], W["end"],
                             bufs["rgc"], bufs["rgby"], bufs["stripe"], bufs["orient"], bufs["line_end"], bufs["padded"],
                             gray, scratch)
-    pts, count = max_value_indices_region(gray, (int(h / region_divisor), int(w / region_divisor)))
+    region = (int(h / region_divisor), int(w / region_divisor))
+    if min(region) >= 1:
+        pts, count = max_value_indices_region(gray, region)
+    else:   # a 1-pixel-high or -wide level has no valid region shape (the reference's max_pool would reject stride 0)
+        pts = np.zeros((0, 4), np.int64)
     bufs.update(gray=gray, points=pts)
     return bufs
 

@@ -666,3 +666,42 @@ def test_pipeline_four_channel_frames(c_oracle, default_filters):
     _check_stack(got, ref, None, "BGRA frames")
     host = pipe.run_host(bgra)
     assert np.array_equal(host.orient, ref["orient"], equal_nan=True) and np.array_equal(host.points, ref["points"])
+
+
+def test_fused_stack_shape_sweep_bit_exact(c_oracle, default_filters):
+    """Level shapes around every tile / vector boundary of the fused kernels (tile widths 48 and 64, tile heights 16 and
+    32, runs of 8, 128-bit rows, bulk-store eligibility w % 4): values, NaN masks and gray bit-equal to the C oracle,
+    including inputs with flat and dark patches (regulator pow path, 0 * inf)."""
+    from pysilent_b200 import LineEndPipeline, _ops
+    weights = LineEndPipeline().stack_weights()
+    rs = np.random.RandomState(404)
+    shapes = [(1, 1, 1), (1, 2, 3), (2, 7, 8), (1, 15, 47), (3, 16, 48), (1, 17, 49), (2, 31, 63), (1, 32, 64), (1, 33, 65),
+              (2, 40, 96), (1, 48, 95), (1, 64, 100), (3, 35, 144), (1, 96, 130)]
+    for n, h, w in shapes:
+        x = (rs.rand(n, h, w, 3) * 255).astype(np.float32)
+        if h > 8 and w > 8:
+            x[0, : h // 3, : w // 2] = 37.0        # flat patch: blurred stripe response < 1 -> pow path
+            x[-1, h // 2:, w // 2:] = 0.0          # dark patch: 0 * inf = NaN
+        orient, line_end, gray = _ops.stack_fused(x, weights)
+        ref = c_oracle.line_end_stack(x, default_filters)
+        assert_bits(orient, ref["orient"], "orient %s" % ((n, h, w),))
+        assert_bits(line_end, ref["padded"], "padded_line_end %s" % ((n, h, w),))
+        assert_bits(gray, ref["gray"], "gray %s" % ((n, h, w),))
+
+
+def test_pipeline_shape_sweep_bit_exact(c_oracle, default_filters):
+    """Frame / level geometries around the fast-path conditions of the pipeline: frame rows that are (not) multiples of 16
+    bytes (frame-pair pyramid kernel vs the per-pixel fallback), level widths that are (not) multiples of 4 / 48 / 64 / 72
+    (bulk stores, tile choices), odd batches (a lone frame in the last pair), levels with unset tail rows. Device-resident
+    and host-buffer calls, values and points bit-equal to the C oracle."""
+    from pysilent_b200 import LineEndPipeline
+    cases = [((97, 131), (24, 16), 2 ** .5, 3), ((120, 160), (72, 48), 1.3, 2), ((121, 163), (50, 34), 1.4, 1),
+             ((200, 304), (76, 52), 1.5, 5), ((333, 448), (144, 96), 1.25, 2), ((480, 640), (100, 66), 1.7, 3)]
+    for shape, center, scale, batch in cases:
+        frames = np.stack([structured_frame(90 + i, *shape) if i % 2 else synthetic_frame(8, i, *shape) for i in range(batch)])
+        pipe = LineEndPipeline(output_size=center, zoom_ratio=scale)
+        pyr, ref = _oracle_pipeline(c_oracle, frames, center, scale, default_filters)
+        res = pipe.run_frames(torch.from_numpy(frames).cuda())
+        _check_stack(res, ref, None, "device %s" % (shape,))
+        host = pipe.run_host(frames)
+        _check_stack(host, ref, None, "host %s" % (shape,))
