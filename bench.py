@@ -190,8 +190,7 @@ def run_ours(args, rank, local_rank, world):
 
     def step():
         pipe.run_frames(frames, out=bufs)
-        if gatherer is not None:
-            gatherer.submit(bufs[2], bufs[3], rank * B)
+        return gatherer.submit(bufs[2], bufs[3], rank * B) if gatherer is not None else None
 
     def barrier():
         if world > 1:
@@ -206,8 +205,11 @@ def run_ours(args, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record()
+    slot = None
     for _ in range(args.steps):
-        step()
+        slot = step()
+    if gatherer is not None and slot is not None:   # the last step's gather (side stream) belongs to the timed region
+        torch.cuda.current_stream().wait_event(gatherer.done[slot])
     ev1.record()
     barrier()
     t_wall1 = time.perf_counter()
