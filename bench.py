@@ -170,6 +170,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = sdist.bind_to_device_numa_node(local_rank)   # page-locked buffers below land next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -291,7 +292,7 @@ def run_ours(args, rank, local_rank, world):
                    "points_per_step": count_points},
         "clocks": clocks,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "numa_node_rank0": numa_node,
                 "api": "LineEndPipeline.run_host -> silent_pipeline_run_host, pinned host buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -6,8 +6,43 @@ data path needs no exchange. Points are tiny (32 B each, a handful per level): t
 issued as one padded ``all_gather`` per batch rather than per frame. Works on any ``torch.distributed`` backend
 (``nccl`` on the GPU box over NVLink, ``gloo`` in the CPU tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def bind_to_device_numa_node(device_index):
+    """Pin this process (CPU affinity, hence first-touch placement of the page-locked frame / result buffers it allocates
+    afterwards) to the NUMA node its GPU hangs off. With one process per GPU on a two-socket host, host<->device copies
+    that cross the socket interconnect cap the end-to-end rate of all ranks together; local buffers do not. Returns the
+    node id, or None when the topology cannot be read (then nothing is changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device_index]) if visible and visible.replace(",", "").isdigit() else device_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml reports an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 def shard_range(total, rank, world_size):
