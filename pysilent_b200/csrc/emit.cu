@@ -2,8 +2,9 @@
 // top-percent mask top_value_points (:8-29).
 //
 // max_value_indices_region: max-pool with ksize = whole level and stride = region (SAME) -> NN-upsample -> value >= up
-// -> tf.where. Here: (1) per-window maxima (NaN-propagating), (2) per-row hit counts, (3) exclusive scan over rows,
-// (4) ordered warp-ballot compaction, so the int64 rows (level, y, x, 0) come out in tf.where's row-major order.
+// -> tf.where. Here: (1) per-window maxima (NaN-propagating; reduced inside stack_b on the fused path), (2) per-row hit
+// counts, (3) exclusive scan over the rows of each level, (4) ordered warp-ballot compaction (a hit row adds up the
+// totals of the levels before it), so the int64 rows (level, y, x, 0) come out in tf.where's row-major order.
 #include "plan.h"
 #include "stack.h"
 
@@ -124,23 +125,35 @@ __global__ void __launch_bounds__(256) scan_level_kernel(int *__restrict__ row_c
     if (threadIdx.x == 0) level_total[blockIdx.x] = s_carry;
 }
 
-// WRITE pass: one warp per row; rows without hits (the vast majority) return at once. Hits are written in x order at
-// level_offset[level] + row_offset[row], i.e. in tf.where's row-major order.
+// WRITE pass: one warp per row; rows without hits (the vast majority) return at once. A row WITH hits first adds up the
+// totals of the levels before its own (a warp-wide sum of at most a few hundred ints: cheaper than a separate scan
+// launch) and then writes its hits in x order at that base + row_offset[row], i.e. in tf.where's row-major order.
+// Warp 0 of block 0 also publishes the grand total.
 __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
                                                          const float *__restrict__ pooled, const int *__restrict__ row_offset,
-                                                         const long long *__restrict__ level_offset,
-                                                         long long *__restrict__ points, long long capacity)
+                                                         const int *__restrict__ level_total, int levels,
+                                                         long long *__restrict__ points, long long capacity,
+                                                         long long *__restrict__ total)
 {
     pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (row == 0) {
+        long long sum = 0;
+        for (int k = lane; k < levels; k += 32) sum += __ldg(level_total + k);
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) *total = sum;
+    }
+    if (row >= rows || capacity <= 0) return;
     const int packed = __ldg(row_offset + row);
     if (!(packed & 0x40000000)) return;
     const int n = row / h, y = row - n * h;
+    long long before = 0;
+    for (int k = lane; k < n; k += 32) before += __ldg(level_total + k);
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
     const float *v = value + (size_t)row * w;
     const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
-    long long base = __ldg(level_offset + n) + (packed & 0x3fffffff);
+    long long base = before + (packed & 0x3fffffff);
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
         bool hit = false;
@@ -156,44 +169,6 @@ __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict
         }
         base += __popc(ballot);
     }
-}
-
-// Single-CTA exclusive scan of the per-row counts (rows = levels * h, at most a few hundred thousand).
-__global__ void __launch_bounds__(1024) scan_rows_kernel(const int *__restrict__ row_count, int rows,
-                                                         long long *__restrict__ row_offset, long long *__restrict__ total)
-{
-    pdl_enter();
-    __shared__ long long s_warp[32];
-    __shared__ long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < rows; base += 1024) {
-        const int i = base + threadIdx.x;
-        const long long mine = i < rows ? row_count[i] : 0;
-        long long incl = mine;
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += up;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            long long wsum = s_warp[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long up = __shfl_up_sync(0xffffffffu, wsum, o);
-                if (lane >= o) wsum += up;
-            }
-            s_warp[lane] = wsum;
-        }
-        __syncthreads();
-        const long long before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - mine;
-        if (i < rows) row_offset[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = before + mine;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = s_carry;
 }
 
 // top_value_points: per-level threshold (1-p)*max + p*min with min = -1 * max(-v); NaN in a level poisons its threshold.
@@ -291,8 +266,7 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     ws += align_up((size_t)n * 4096 * sizeof(float), 256);
     int *row_offset = (int *)ws;            // offset of each row within its level
     ws += align_up((size_t)rows * sizeof(int), 256);
-    long long *level_offset = (long long *)ws;
-    ws += align_up((size_t)n * sizeof(long long), 256);
+    ws += align_up((size_t)n * sizeof(long long), 256);   // (reserved)
     int *level_total = (int *)ws;
 
     if (fused_winmax) {
@@ -309,15 +283,11 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     SILENT_LAUNCH_CHECK("count_rows_kernel");
     SILENT_CUDA(launch_dependent(scan_level_kernel, dim3(n), dim3(256), 0, stream, row_offset, h, level_total));
     SILENT_LAUNCH_CHECK("scan_level_kernel");
-    SILENT_CUDA(launch_dependent(scan_rows_kernel, dim3(1), dim3(1024), 0, stream, (const int *)level_total, n, level_offset,
-                                 (long long *)count));
-    SILENT_LAUNCH_CHECK("scan_rows_kernel");
-    if (capacity > 0) {
-        SILENT_CUDA(launch_dependent(write_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
-                                     (const float *)pooled, (const int *)row_offset, (const long long *)level_offset,
-                                     (long long *)points, (long long)capacity));
-        SILENT_LAUNCH_CHECK("write_rows_kernel");
-    }
+    // (also when capacity == 0: the kernel publishes the total)
+    SILENT_CUDA(launch_dependent(write_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
+                                 (const float *)pooled, (const int *)row_offset, (const int *)level_total, n,
+                                 (long long *)points, (long long)capacity, (long long *)count));
+    SILENT_LAUNCH_CHECK("write_rows_kernel");
     return SILENT_OK;
 }
 
