@@ -69,6 +69,11 @@ def lib():
         L.so_line_end_stack.restype = None
         L.so_line_end_stack.argtypes = [_f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p, c_int, _f32p] + \
             [_f32p] * 8
+        L.so_line_end_stack_fused.restype = None
+        L.so_line_end_stack_fused.argtypes = L.so_line_end_stack.argtypes
+        for name in ("so_depthwise3", "so_rgby_shared", "so_stripe_sym180", "so_end_ownoth"):
+            getattr(L, name).restype = c_int
+            getattr(L, name).argtypes = [_f32p]
         L.so_get_centroids.restype = None
         L.so_get_centroids.argtypes = [_f32p, c_int, c_int, c_int, c_int, c_int, _f32p, _f32p, _f32p]
         L.so_resize_nearest.restype = None
@@ -184,7 +189,11 @@ def top_value_points(color, value, top_percent=0.1):
     return out
 
 
-def line_end_stack(pyramid, weights, region_divisor=2.0):
+def line_end_stack(pyramid, weights, region_divisor=2.0, order="fused"):
+    """S1-S8 on an NHWC pyramid. ``order``: "fused" = the canonical order of the fused stack kernels (structured
+    convolutions evaluated through their shared sub-kernels, so_line_end_stack_fused); "operator" = every stage as the
+    stand-alone operator evaluates it (one (ky, ci, kx) chain per output, so_line_end_stack)."""
+    assert order in ("fused", "operator")
     x = _c(pyramid)
     n, h, w, ch = x.shape
     assert ch == 3
@@ -192,9 +201,9 @@ def line_end_stack(pyramid, weights, region_divisor=2.0):
     bufs = {k: np.empty_like(x) for k in ("rgc", "rgby", "stripe", "orient", "line_end", "padded")}
     gray = np.empty((n, h, w, 1), np.float32)
     scratch = np.empty((2,) + x.shape, np.float32)
-    lib().so_line_end_stack(x, n, h, w, W["rgc"], W["rgby"], W["stripe"], W["blur"], W["blur"].shape[0], W["end"],
-                            bufs["rgc"], bufs["rgby"], bufs["stripe"], bufs["orient"], bufs["line_end"], bufs["padded"],
-                            gray, scratch)
+    fn = lib().so_line_end_stack_fused if order == "fused" else lib().so_line_end_stack
+    fn(x, n, h, w, W["rgc"], W["rgby"], W["stripe"], W["blur"], W["blur"].shape[0], W["end"],
+       bufs["rgc"], bufs["rgby"], bufs["stripe"], bufs["orient"], bufs["line_end"], bufs["padded"], gray, scratch)
     region = (int(h / region_divisor), int(w / region_divisor))
     if min(region) >= 1:
         pts, count = max_value_indices_region(gray, region)

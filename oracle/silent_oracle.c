@@ -365,6 +365,165 @@ void so_line_end_stack(const float *pyr, int N, int h, int w, const float *rgc, 
 }
 
 /* ---------------------------------------------------------------------------------------------------------------- */
+/* FUSED canonical order: the composition above with the three structured convolutions evaluated the way the fused   */
+/* stack kernels do (pysilent_b200/csrc/stack_fused.cu). The structures are properties of the reference's own weight */
+/* generators and are detected BITWISE on the float32 weights; a filter without its structure    */
+/* takes the generic (ky, ci, kx) chain of so_conv2d. Same math as the reference graph, fewer roundings.             */
+/* ---------------------------------------------------------------------------------------------------------------- */
+
+#define W4(wt, t, ci, co) ((wt)[((t) * 3 + (ci)) * 3 + (co)])
+
+/* midget_rgc: only ci == co slices are non-zero (skipping exact zeros is a no-op for finite inputs) */
+int so_depthwise3(const float *wt)
+{
+    for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < 3; ++ci)
+            for (int co = 0; co < 3; ++co)
+                if (ci != co && W4(wt, t, ci, co) != 0.0f) return 0;
+    return 1;
+}
+
+/* rgby_3: off-centre taps couple every pair of DIFFERENT channels through one kernel S (doubled for the pair 1 <-> 2);
+ * the centre tap holds d_i on the diagonal and e between channels 1 and 2 (cc/center_surround/rgby.py:36-56). */
+int so_rgby_shared(const float *wt)
+{
+    if (!bits_equal(W4(wt, 4, 0, 1), 0.0f)) return 0;
+    for (int t = 0; t < 9; ++t) {
+        float sv = W4(wt, t, 0, 1);
+        if (!bits_equal(W4(wt, t, 0, 2), sv) || !bits_equal(W4(wt, t, 1, 0), sv) || !bits_equal(W4(wt, t, 2, 0), sv))
+            return 0;
+        if (t != 4) {
+            if (!bits_equal(W4(wt, t, 1, 2), 2.0f * sv) || !bits_equal(W4(wt, t, 2, 1), 2.0f * sv)) return 0;
+            for (int c = 0; c < 3; ++c)
+                if (!bits_equal(W4(wt, t, c, c), 0.0f)) return 0;
+        }
+    }
+    return 1;
+}
+
+/* T_i = chain over the 8 off-centre taps of S on channel i (tap order ascending); u0 = d0 a0 + (T1 + T2);
+ * u1 = d1 a1 + (e21 a2 + (2 T2 + T0)); u2 = d2 a2 + (e12 a1 + (2 T1 + T0)); each step one fmaf; relu. */
+static void so_conv_rgby_shared(const float *a, int N, int h, int w, const float *wt, float *out)
+{
+    const float d0 = W4(wt, 4, 0, 0), d1 = W4(wt, 4, 1, 1), d2 = W4(wt, 4, 2, 2), e12 = W4(wt, 4, 1, 2),
+                e21 = W4(wt, 4, 2, 1);
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                float T[3] = {0.0f, 0.0f, 0.0f};
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int t = 0; t < 9; ++t) {
+                        if (t == 4) continue;
+                        int sy = y + t / 3 - 1, sx = x + t % 3 - 1;
+                        int inside = sy >= 0 && sy < h && sx >= 0 && sx < w;
+                        float v = inside ? a[(((size_t)n * h + sy) * w + sx) * 3 + ci] : 0.0f;
+                        T[ci] = fmaf(W4(wt, t, 0, 1), v, T[ci]);
+                    }
+                const float *c = a + (((size_t)n * h + y) * w + x) * 3;
+                float u0 = fmaf(d0, c[0], T[1] + T[2]);
+                float u1 = fmaf(d1, c[1], fmaf(e21, c[2], fmaf(2.0f, T[2], T[0])));
+                float u2 = fmaf(d2, c[2], fmaf(e12, c[1], fmaf(2.0f, T[1], T[0])));
+                float *o = out + (((size_t)n * h + y) * w + x) * 3;
+                o[0] = u0 < 0.0f ? 0.0f : u0;
+                o[1] = u1 < 0.0f ? 0.0f : u1;
+                o[2] = u2 < 0.0f ? 0.0f : u2;
+            }
+}
+
+/* rgb_2d_stripe_tensors: identical over the input channel and K[ky][kx] == K[2-ky][2-kx] */
+int so_stripe_sym180(const float *wt)
+{
+    if (!so_uniform_in(wt, 3, 3, 3)) return 0;
+    for (int t = 0; t < 4; ++t)
+        for (int co = 0; co < 3; ++co)
+            if (!bits_equal(W4(wt, t, 0, co), W4(wt, 8 - t, 0, co))) return 0;
+    return 1;
+}
+
+/* on the channel sum s = (b0 + b1) + b2: chain over (s[-1,-1] + s[1,1]), (s[-1,0] + s[1,0]), (s[-1,1] + s[1,-1]),
+ * (s[0,-1] + s[0,1]), s[0,0] with the weights of taps 0..4; relu. */
+static void so_conv_stripe_sym(const float *b, int N, int h, int w, const float *wt, float *out)
+{
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                float s[9];
+                for (int t = 0; t < 9; ++t) {
+                    int sy = y + t / 3 - 1, sx = x + t % 3 - 1;
+                    if (sy >= 0 && sy < h && sx >= 0 && sx < w) {
+                        const float *px = b + (((size_t)n * h + sy) * w + sx) * 3;
+                        s[t] = (px[0] + px[1]) + px[2];
+                    } else {
+                        s[t] = 0.0f;
+                    }
+                }
+                const float p[5] = {s[0] + s[8], s[1] + s[7], s[2] + s[6], s[3] + s[5], s[4]};
+                for (int co = 0; co < 3; ++co) {
+                    float acc = 0.0f;
+                    for (int t = 0; t < 5; ++t) acc = fmaf(W4(wt, t, 0, co), p[t], acc);
+                    out[(((size_t)n * h + y) * w + x) * 3 + co] = acc < 0.0f ? 0.0f : acc;
+                }
+            }
+}
+
+/* rgb_2d_end_tensors: input channel ci reaches the two other output channels through the same kernel */
+int so_end_ownoth(const float *wt)
+{
+    for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < 3; ++ci)
+            if (!bits_equal(W4(wt, t, ci, (ci + 1) % 3), W4(wt, t, ci, (ci + 2) % 3))) return 0;
+    return 1;
+}
+
+/* per input channel an "own" and an "other" chain over the 9 taps; e_co = (t_0 + t_1) + t_2, t_ci = own or other;
+ * relu, clip at clip_hi. */
+static void so_conv_end_ownoth(const float *d, int N, int h, int w, const float *wt, float clip_hi, float *out)
+{
+    for (int n = 0; n < N; ++n)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                float own[3], oth[3];
+                for (int ci = 0; ci < 3; ++ci) {
+                    own[ci] = oth[ci] = 0.0f;
+                    for (int t = 0; t < 9; ++t) {
+                        int sy = y + t / 3 - 1, sx = x + t % 3 - 1;
+                        int inside = sy >= 0 && sy < h && sx >= 0 && sx < w;
+                        float v = inside ? d[(((size_t)n * h + sy) * w + sx) * 3 + ci] : 0.0f;
+                        own[ci] = fmaf(W4(wt, t, ci, ci), v, own[ci]);
+                        oth[ci] = fmaf(W4(wt, t, ci, (ci + 1) % 3), v, oth[ci]);
+                    }
+                }
+                for (int co = 0; co < 3; ++co) {
+                    float acc = co == 0 ? own[0] : oth[0];
+                    acc = acc + (co == 1 ? own[1] : oth[1]);
+                    acc = acc + (co == 2 ? own[2] : oth[2]);
+                    acc = acc < 0.0f ? 0.0f : acc;
+                    acc = acc > clip_hi ? clip_hi : acc;
+                    out[(((size_t)n * h + y) * w + x) * 3 + co] = acc;
+                }
+            }
+}
+
+/* Same buffers as so_line_end_stack. Which stage takes its structured order mirrors the kernels' dispatch:
+ * S2 shared needs a depthwise rgc as well (one stack_a variant), S3 symmetric and S5 own/other go together. */
+void so_line_end_stack_fused(const float *pyr, int N, int h, int w, const float *rgc, const float *rgby,
+                             const float *stripe, const float *blur, int blur_k, const float *end, float *a, float *b,
+                             float *c, float *orient, float *line_end, float *padded, float *gray, float *scratch)
+{
+    so_conv2d(pyr, N, h, w, 3, rgc, 3, 3, 3, 1, 0.0f, a);
+    if (so_depthwise3(rgc) && so_rgby_shared(rgby)) so_conv_rgby_shared(a, N, h, w, rgby, b);
+    else so_conv2d(a, N, h, w, 3, rgby, 3, 3, 3, 1, 0.0f, b);
+    const int structured = so_stripe_sym180(stripe) && so_end_ownoth(end);
+    if (structured) so_conv_stripe_sym(b, N, h, w, stripe, c);
+    else so_conv2d(b, N, h, w, 3, stripe, 3, 3, 3, 1, 0.0f, c);
+    so_regulate(c, N, h, w, 3, blur, blur_k, 1.0f, 0.1f, scratch, orient);
+    if (structured) so_conv_end_ownoth(orient, N, h, w, end, 255.0f, line_end);
+    else so_conv2d(orient, N, h, w, 3, end, 3, 3, 3, 2, 255.0f, line_end);
+    so_pad_inwards(line_end, N, h, w, 3, 2, 2, 2, 2, padded);
+    so_value_from_color(padded, (size_t)N * h * w, 3, gray);
+}
+
+/* ---------------------------------------------------------------------------------------------------------------- */
 /* "next" rows: centroids (util/centroids.py:21-71), nearest resize, boosting (util/energy/boosting.py)  */
 /*                                                                                                                  */
 /* Canonical order: block sums are float32 add chains from +0 over the window in (ky, kx) order (out-of-image taps    */

@@ -70,8 +70,12 @@ __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict
 
 // One warp per row (level, y). Pass 0 counts hits, pass 1 writes them at row_offset in x order.
 // COUNT pass: one warp per row (level, y); 128-bit loads when the row length allows; writes the row's hit count.
+// With the per-tile maxima that stack_b_kernel leaves behind, a row first asks whether ANY of its tiles can hold a hit
+// (tile maximum >= the smallest region maximum the tile is compared with); on generic input a handful of tiles per level
+// can, so almost every row returns without touching `value` at all.
 __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
-                                                         const float *__restrict__ pooled, int *__restrict__ row_count)
+                                                         const float *__restrict__ pooled, int *__restrict__ row_count,
+                                                         TileMaxima tm)
 {
     pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -80,6 +84,26 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict
     const int n = row / h, y = row - n * h;
     const float *v = value + (size_t)row * w;
     const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
+    if (tm.data) {
+        const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
+        bool any = false;
+        for (int t0 = 0; t0 < tm.ntx; t0 += 32) {
+            const int tx = t0 + lane;
+            bool cand = false;
+            if (tx < tm.ntx) {
+                const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w) - 1;
+                const int best = __ldg(tile_row + tx);
+                cand = best == 0x7fc00000;   // a NaN somewhere in the tile: let the exact pass decide
+                const float bf = __int_as_float(best);
+                for (int j = nearest_src(x0, g.sx, g.ow); j <= nearest_src(x1, g.sx, g.ow); ++j) cand |= bf >= __ldg(pool_row + j);
+            }
+            any |= __any_sync(0xffffffffu, cand);
+        }
+        if (!any) {
+            if (lane == 0) row_count[row] = 0;
+            return;
+        }
+    }
     int hits = 0;
     if ((w & 3) == 0) {
         for (int q = lane; q < (w >> 2); q += 32) {
@@ -247,7 +271,7 @@ bool window_geometry(int h, int w, int region_h, int region_w, WindowGeom *geo)
 
 int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
                              int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
-                             const int *fused_winmax, cudaStream_t stream)
+                             const int *fused_winmax, const TileMaxima *tiles, cudaStream_t stream)
 {
     if (!value || !count || !workspace || (!points && capacity > 0))
         return fail(SILENT_E_INVAL, "silent_max_value_indices_region: null argument");
@@ -279,7 +303,7 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
     const unsigned blocks = (unsigned)ceil_div(rows, 8);
     SILENT_CUDA(launch_dependent(count_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
-                                 (const float *)pooled, row_offset));
+                                 (const float *)pooled, row_offset, tiles ? *tiles : TileMaxima()));
     SILENT_LAUNCH_CHECK("count_rows_kernel");
     SILENT_CUDA(launch_dependent(scan_level_kernel, dim3(n), dim3(256), 0, stream, row_offset, h, level_total));
     SILENT_LAUNCH_CHECK("scan_level_kernel");
@@ -308,7 +332,7 @@ int silent_max_value_indices_region(const float *value_dev, int n, int h, int w,
                                     size_t workspace_bytes, silent_stream stream)
 {
     return max_value_indices_region(value_dev, n, h, w, region_h, region_w, points_dev, capacity, count_dev,
-                                    workspace_dev, workspace_bytes, nullptr, (cudaStream_t)stream);
+                                    workspace_dev, workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int silent_top_value_points(const float *color_dev, const float *value_dev, int n, int h, int w, int c,

@@ -19,6 +19,7 @@ static void release(Workspace &ws)
     cudaFree(ws.d_select);
     cudaFree(ws.d_stack);
     cudaFree(ws.d_winmax);
+    cudaFree(ws.d_tilemax);
     cudaFree(ws.d_points);
     cudaFree(ws.d_count);
     cudaFreeHost(ws.h_frames);
@@ -94,6 +95,11 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     ws.stack_bytes = stack_workspace_bytes((int)n, plan->h, plan->w);
     SILENT_CUDA(cudaMalloc(&ws.d_stack, ws.stack_bytes));
     SILENT_CUDA(cudaMalloc(&ws.d_winmax, n * 4 * sizeof(int)));
+    {
+        int th, tw, nty, ntx;
+        stack_tile_grid(plan->h, plan->w, &th, &tw, &nty, &ntx);
+        SILENT_CUDA(cudaMalloc(&ws.d_tilemax, n * nty * ntx * sizeof(int)));
+    }
     SILENT_CUDA(cudaMalloc(&ws.d_points, ws.points_capacity * 4 * sizeof(int64_t)));
     SILENT_CUDA(cudaMalloc(&ws.d_count, sizeof(int64_t)));
     // h_frames / h_orient / h_line_end (pinned mirrors for PAGEABLE caller buffers) are allocated on first need
@@ -101,6 +107,15 @@ int silent_plan_reserve(silent_plan *plan, int max_batch)
     SILENT_CUDA(cudaMallocHost(&ws.h_count, sizeof(int64_t)));
     ws.batch = max_batch;
     return SILENT_OK;
+}
+
+// the per-tile maxima of gray that stack_b_kernel writes for the whole batch (read by the emit stage)
+static TileMaxima tile_maxima(const silent_plan *plan)
+{
+    TileMaxima tm;
+    stack_tile_grid(plan->h, plan->w, &tm.tile_h, &tm.tile_w, &tm.nty, &tm.ntx);
+    tm.data = plan->ws.d_tilemax;
+    return tm;
 }
 
 // K1 + K2 for frames [frame0, frame0 + nb) of a batch: the outputs, gray and the region maxima of these frames land at
@@ -131,11 +146,12 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
     const void *pyr = pair_path ? (const void *)ws.d_pyramid
                                 : (const void *)(pyramid_dev ? pyramid_dev + img0 * level_elems * 3 : ws.d_pyramid);
     if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
+    const TileMaxima tm = tile_maxima(plan);
     return stack_fused(pyr, n, plan->h, plan->w, pair_path ? plan->levels : 0, W,
                        orient_dev ? orient_dev + img0 * level_elems * 3 : nullptr,
                        line_end_dev ? line_end_dev + img0 * level_elems * 3 : nullptr, ws.d_gray + img0 * level_elems,
-                       ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr, s,
-                       plan->timing ? plan->ev_mid : nullptr);
+                       ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr,
+                       ws.d_tilemax + img0 * tm.nty * tm.ntx, s, plan->timing ? plan->ev_mid : nullptr);
 }
 
 static int check_pipeline_args(const silent_plan *plan, const silent_stack_weights *W, const void *frames, int batch)
@@ -170,9 +186,11 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
                           fuse_windows ? &geo : nullptr, s);
     if (rc != SILENT_OK) return rc;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
-    if (count_dev)
+    if (count_dev) {
+        const TileMaxima tm = tile_maxima(plan);
         rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
-                                      count_dev, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, s);
+                                      count_dev, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, &tm, s);
+    }
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[3], s));
     return rc;
 }
@@ -292,8 +310,9 @@ int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weig
         return rc;
     }
     const int64_t cap = capacity < ws.points_capacity ? capacity : ws.points_capacity;
+    const TileMaxima tm = tile_maxima(plan);
     rc = max_value_indices_region(ws.d_gray, (int)n, plan->h, plan->w, plan->h / 2, plan->w / 2, ws.d_points, cap,
-                                  ws.d_count, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, s);
+                                  ws.d_count, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, &tm, s);
     if (rc == SILENT_OK) {
         SILENT_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         if (points_host && cap > 0)

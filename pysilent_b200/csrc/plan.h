@@ -40,6 +40,7 @@ struct Workspace {
     void *d_stack = nullptr;       // fused-stack workspace (paired channel-sum tensor)
     size_t stack_bytes = 0;
     int *d_winmax = nullptr;       // [B*L][<=4] per-region maxima reduced inside the stack kernel
+    int *d_tilemax = nullptr;      // [B*L][tile rows][tile cols] per-tile maxima of gray (stack_b -> emit)
     int64_t *d_points = nullptr;   // [points_capacity][4]
     int64_t points_capacity = 0;
     int64_t *d_count = nullptr;

@@ -16,7 +16,13 @@ struct WindowGeom {
 size_t stack_workspace_bytes(int n, int h, int w);
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
-                int *winmax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr);
+                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr);
+// tile grid of stack_b_kernel; tilemax is int [n][nty][ntx] (ordered-int maxima of gray per tile, NaN = 0x7fc00000)
+void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx);
+struct TileMaxima {
+    const int *data = nullptr;   // null: every tile is scanned
+    int tile_h = 0, tile_w = 0, nty = 0, ntx = 0;
+};
 
 // pyramid.cu
 int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
@@ -28,7 +34,7 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
 bool window_geometry(int h, int w, int region_h, int region_w, WindowGeom *geo);
 int max_value_indices_region(const float *value, int n, int h, int w, int region_h, int region_w, int64_t *points,
                              int64_t capacity, int64_t *count, void *workspace, size_t workspace_bytes,
-                             const int *fused_winmax, cudaStream_t stream);
+                             const int *fused_winmax, const TileMaxima *tiles, cudaStream_t stream);
 size_t selection_bytes(int n, int h, int w);
 
 }  // namespace silent

@@ -26,6 +26,7 @@
 // issue and shared-memory bandwidth rather than HBM.
 #include <cuda.h>
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
@@ -55,7 +56,7 @@ __device__ __forceinline__ float clip_nan(float v, float hi)
     asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(v), "f"(hi));
     return r;
 }
-__device__ __forceinline__ f2 relu2_finite(f2 v) { return make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)); }
+__device__ __forceinline__ f2 relu2_finite(f2 v) { return make_float2(relu_nan(v.x), relu_nan(v.y)); }
 __device__ __noinline__ float slow_gain(float m, float value, float root) { return canon_gain(m, value, root); }
 
 constexpr int kPX = 8;   // pixels per thread run
@@ -200,6 +201,8 @@ __device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[
 struct ParamsA {
     f2 w1[9][3][3];   // rgc  [tap][ci][co] as (w, w)
     f2 w2[9][3][3];   // rgby
+    f2 s2s[9];        // S2 mode 2: the shared surround kernel S (centre tap unused)
+    f2 s2c[6];        // S2 mode 2: centre taps d0, d1, d2 (ci -> ci), e12 (1 -> 2), e21 (2 -> 1), and the constant 2
     int h, w, n;      // level shape, number of images
     int pair_levels;  // image pairing: pair p holds images (a, a + pair_levels), see pair_images()
     int use_tma;      // PAIRED_IN only: load the tile with one TMA box copy
@@ -241,7 +244,12 @@ __host__ __device__ constexpr bool rgby_nonzero(int tap, int ci, int co)
 
 // PAIRED_IN: the input is xpair[pair][c][y][x] float2 written by pyramid_pair_kernel (a verbatim 128-bit copy into the
 // planes); otherwise it is an NHWC float32 pyramid [n][h][w][3] (stand-alone silent_stack_fused).
-template <int TH, int TW, int NT, bool S1_DEPTHWISE, bool S2_RGBY, bool PAIRED_IN>
+// S2 modes: 0 dense; 1 rgby_3 zero pattern (28 structural zeros skipped, 53 FFMA2 per pixel pair); 2 rgby_3 SHARED
+// surround: off-centre taps couple every channel pair (i != j) through ONE kernel S, doubled for the
+// pair (1, 2), and the centre tap carries d_i on the diagonal plus e between channels 1 and 2. Then
+//   T_i = S * a_i  (8 taps each),   u0 = d0 a0 + (T1 + T2),   u1 = d1 a1 + (e21 a2 + (2 T2 + T0)),   u2 likewise:
+// 24 + 8 FFMA2/FADD2 instead of 53. Part of the canonical FUSED order (oracle/silent_oracle.c: so_rgby_shared).
+template <int TH, int TW, int NT, bool S1_DEPTHWISE, int S2_MODE, bool PAIRED_IN>
 __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ input, const __grid_constant__ ParamsA P,
                                                      const __grid_constant__ CUtensorMap tmap, f2 *__restrict__ bsum2)
 {
@@ -443,29 +451,60 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
         const int r = t % TH, k = t / TH;
         const int gy = ty0 + r, gx0 = tx0 + kPX * k;
         if (gy >= h || gx0 >= w) continue;
-        f2 acc[kPX][3];
-#pragma unroll
-        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        f2 s[kPX];
+        if constexpr (S2_MODE == 2) {
+            f2 T[3][kPX], ctr[3][kPX];
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                f2 v[10];
-                load_cols<5>(sA + ci * T::A_PLANE + (r + ky) * T::A_PITCH + kPX * k, v);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
+                for (int p = 0; p < kPX; ++p) T[ci][p] = zero2();
 #pragma unroll
-                    for (int p = 0; p < kPX; ++p)
+                for (int ky = 0; ky < 3; ++ky) {
+                    f2 v[10];
+                    load_cols<5>(sA + ci * T::A_PLANE + (r + ky) * T::A_PITCH + kPX * k, v);
 #pragma unroll
-                        for (int co = 0; co < 3; ++co)
-                            if (!S2_RGBY || rgby_nonzero(ky * 3 + kx, ci, co))
-                                acc[p][co] = fma2(P.w2[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        if (ky == 1 && kx == 1) {
+#pragma unroll
+                            for (int p = 0; p < kPX; ++p) ctr[ci][p] = v[p + 1];
+                        } else {
+#pragma unroll
+                            for (int p = 0; p < kPX; ++p) T[ci][p] = fma2(P.s2s[ky * 3 + kx], v[p + kx], T[ci][p]);
+                        }
+                    }
+                }
             }
-        }
-        f2 s[kPX];
 #pragma unroll
-        for (int p = 0; p < kPX; ++p)
-            s[p] = add2(add2(relu2_finite(acc[p][0]), relu2_finite(acc[p][1])), relu2_finite(acc[p][2]));
+            for (int p = 0; p < kPX; ++p) {
+                const f2 u0 = fma2(P.s2c[0], ctr[0][p], add2(T[1][p], T[2][p]));
+                const f2 u1 = fma2(P.s2c[1], ctr[1][p], fma2(P.s2c[4], ctr[2][p], fma2(P.s2c[5], T[2][p], T[0][p])));
+                const f2 u2 = fma2(P.s2c[2], ctr[2][p], fma2(P.s2c[3], ctr[1][p], fma2(P.s2c[5], T[1][p], T[0][p])));
+                s[p] = add2(add2(relu2_finite(u0), relu2_finite(u1)), relu2_finite(u2));
+            }
+        } else {
+            f2 acc[kPX][3];
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    f2 v[10];
+                    load_cols<5>(sA + ci * T::A_PLANE + (r + ky) * T::A_PITCH + kPX * k, v);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                            for (int co = 0; co < 3; ++co)
+                                if (S2_MODE == 0 || rgby_nonzero(ky * 3 + kx, ci, co))
+                                    acc[p][co] = fma2(P.w2[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kPX; ++p)
+                s[p] = add2(add2(relu2_finite(acc[p][0]), relu2_finite(acc[p][1])), relu2_finite(acc[p][2]));
+        }
         // staged in shared memory (over the x planes, dead since S1) and written out row-contiguously below: a run is
         // 64 B of ONE row, so storing it from here would touch 32 different rows per instruction
         store_cols8(sOut + r * T::O_PITCH + kPX * k, s);
@@ -496,10 +535,11 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
 // ---------------------------------------------------------------------------------------------------------------------
 
 struct ParamsB {
-    f2 w3[9][3];      // stripe [tap][co]  (identical over ci)
+    f2 w3[9][3];      // stripe [tap][co]  (identical over ci); SYM3: taps 0..4 = the five distinct weights, see S3
     f2 wb[49];        // blur   [tap]      (identical over ci, co)
-    f2 w5[9][3][3];   // end    [tap][ci][co]
+    f2 w5[9][3][3];   // end    [tap][ci][co]; OWNOTH: [tap][ci][0] = ci -> ci, [tap][ci][1] = ci -> each other channel
     float reg_value, reg_root, clip_max;
+    float quick_thr;  // S4 early-out: a channel sum >= quick_thr under ANY blur tap proves m >= 1 (0: early-out disabled)
     int border;
     int h, w, n;
     int pair_levels;  // see pair_images()
@@ -525,15 +565,24 @@ struct TileB {
     static constexpr int STAGE_F2 = 2 * TH * ST_PITCH / 2;            // float2 slots
     static constexpr int G_PITCH = TW + 4;                            // floats per staged gray row (odd multiple of 16 B)
     static constexpr int FRONT_F2 = B_PLANE + CS_PLANE > STAGE_F2 ? B_PLANE + CS_PLANE : STAGE_F2;
-    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE) * sizeof(f2) + 64;
+    // maxima of the stripe channel sum over aligned groups of 4 columns ("quads", origin -4): the S4 early-out reads
+    // 7 rows x 3 quads instead of 7 x 14 values. Two spare quads per row (never computed, always "large").
+    static constexpr int Q_PITCH = round_pitch(2 * C_RUNS + 2);
+    static constexpr int Q_PLANE = CS_ROWS * Q_PITCH;
+    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE + Q_PLANE) * sizeof(f2) + 64;
     static_assert(TW % kPX == 0, "tile width must be a multiple of the run length");
 };
 
-template <int TH, int TW, int NT>
+// SYM3: every stripe kernel is symmetric under a 180-degree rotation (K[ky][kx] == K[2-ky][2-kx], true for
+// rgb_2d_stripe_tensors): opposite taps are added first, 4 FADD2 + 15 FFMA2 per pixel pair instead of 27 FFMA2.
+// OWNOTH: an input channel of the end filter feeds the two OTHER output channels with one and the same 3x3 kernel (true
+// for rgb_2d_end_tensors): per input channel one "own" and one "other" chain, 54 FFMA2 + 6 FADD2 instead of 81 FFMA2.
+// Both orders are part of the canonical FUSED evaluation order (oracle/silent_oracle.c: so_line_end_stack_fused).
+template <int TH, int TW, int NT, bool SYM3, bool OWNOTH>
 __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
                                                      const __grid_constant__ CUtensorMap tmap, float *__restrict__ orient,
                                                      float *__restrict__ line_end, float *__restrict__ gray,
-                                                     int *__restrict__ winmax)
+                                                     int *__restrict__ winmax, int *__restrict__ tilemax)
 {
     using T = TileB<TH, TW>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -542,8 +591,9 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
     f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
+    f2 *sQ = sCD + 3 * T::CD_PLANE;              // [CS_ROWS][Q_PITCH]      quad maxima of sCs, origin (-4, -4)
     float *sStage = reinterpret_cast<float *>(sB);   // [2][TH][ST_PITCH] NHWC staging, valid after the S4 barrier
-    int *sWin = reinterpret_cast<int *>(sCD + 3 * T::CD_PLANE);   // [2 images][4 windows]
+    int *sWin = reinterpret_cast<int *>(sQ + T::Q_PLANE);   // [2 images][4 windows] + [2 images] tile maxima
     float *sGray = reinterpret_cast<float *>(sCD);                // [2][TH][G_PITCH] gray staging, valid after the S5 barrier
 
     const int tid = threadIdx.x;
@@ -558,7 +608,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     bool has_b;
     pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
 
-    if (tid < 8) sWin[tid] = 0;
+    if (tid < 10) sWin[tid] = 0;
 
     // ---- load the channel-sum tile (pairs are already interleaved): one TMA box [B_ROWS][B_PITCH], zero outside -------
     if (P.use_tma) {
@@ -605,16 +655,46 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
 #pragma unroll
         for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
         if (gy >= 0 && gy < h) {
+            if constexpr (SYM3) {
+                // chain over (b[-1,-1] + b[1,1]), (b[-1,0] + b[1,0]), (b[-1,1] + b[1,-1]), (b[0,-1] + b[0,1]), b[0,0]
+                {
+                    f2 v0[10], v2[10];
+                    load_cols<5>(sB + r * T::B_PITCH + kPX * k, v0);
+                    load_cols<5>(sB + (r + 2) * T::B_PITCH + kPX * k, v2);
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                f2 v[10];
-                load_cols<5>(sB + (r + ky) * T::B_PITCH + kPX * k, v);
+                    for (int p = 0; p < kPX; ++p) {
+                        const f2 p1 = add2(v0[p], v2[p + 2]), p2 = add2(v0[p + 1], v2[p + 1]), p3 = add2(v0[p + 2], v2[p]);
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
+                        for (int co = 0; co < 3; ++co) {
+                            acc[p][co] = fma2(P.w3[0][co], p1, acc[p][co]);
+                            acc[p][co] = fma2(P.w3[1][co], p2, acc[p][co]);
+                            acc[p][co] = fma2(P.w3[2][co], p3, acc[p][co]);
+                        }
+                    }
+                }
+                f2 v1[10];
+                load_cols<5>(sB + (r + 1) * T::B_PITCH + kPX * k, v1);
 #pragma unroll
-                    for (int p = 0; p < kPX; ++p)
+                for (int p = 0; p < kPX; ++p) {
+                    const f2 p4 = add2(v1[p], v1[p + 2]);
 #pragma unroll
-                        for (int co = 0; co < 3; ++co) acc[p][co] = fma2(P.w3[ky * 3 + kx][co], v[p + kx], acc[p][co]);
+                    for (int co = 0; co < 3; ++co) {
+                        acc[p][co] = fma2(P.w3[3][co], p4, acc[p][co]);
+                        acc[p][co] = fma2(P.w3[4][co], v1[p + 1], acc[p][co]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    f2 v[10];
+                    load_cols<5>(sB + (r + ky) * T::B_PITCH + kPX * k, v);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                            for (int co = 0; co < 3; ++co) acc[p][co] = fma2(P.w3[ky * 3 + kx][co], v[p + kx], acc[p][co]);
+                }
             }
         }
         f2 cs[kPX];
@@ -636,6 +716,19 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             }
         }
         store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
+        {   // quad maxima for the S4 early-out; a quad that lies wholly outside the level can only serve pixels outside
+            // the level (whose d is 0 whatever m is): it reads "large" so that it never forces the slow path
+            const float big = 3.0e38f;
+            f2 q0 = make_float2(fmaxf(fmaxf(cs[0].x, cs[1].x), fmaxf(cs[2].x, cs[3].x)),
+                                fmaxf(fmaxf(cs[0].y, cs[1].y), fmaxf(cs[2].y, cs[3].y)));
+            f2 q1 = make_float2(fmaxf(fmaxf(cs[4].x, cs[5].x), fmaxf(cs[6].x, cs[7].x)),
+                                fmaxf(fmaxf(cs[4].y, cs[5].y), fmaxf(cs[6].y, cs[7].y)));
+            if (gx0 + 3 < 0 || gx0 >= w) q0 = make_float2(big, big);
+            if (gx0 + 7 < 0 || gx0 + 4 >= w) q1 = make_float2(big, big);
+            float4 *qd = reinterpret_cast<float4 *>(sQ + r * T::Q_PITCH + 2 * k);
+            qd[0] = make_float4(q0.x, q0.y, q1.x, q1.y);
+            if (k == T::C_RUNS - 1) qd[1] = make_float4(big, big, big, big);   // the two spare quads of this row
+        }
         const int rd = r - 3;   // row in the CD planes (origin -1)
         if (rd >= 0 && rd < T::CD_ROWS) {
             // column -4 + 8k + p sits at idx = 8k - 3 + p of the CD planes (origin -1): odd p starts an aligned pair
@@ -666,6 +759,41 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
 #pragma unroll
             for (int co = 0; co < 3; ++co) store_cols8(sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k, z);
             continue;
+        }
+        if (P.quick_thr > 0.0f) {
+            // Early-out. Every blur weight is positive and every stripe response is >= 0 and finite here, so the blur
+            // chain never decreases: m >= rn(w_min * c) for ANY c of the window. A pixel's aligned quad of columns lies
+            // inside its 7x7 window, so "the quad's maximum over the 7 window rows reaches quick_thr" proves m >= 1, where
+            // the gain is exactly reg_value (gaussian_regulator_tensor.py:35: min(m, 1)) -- bit-identical to the long way.
+            f2 qa = zero2(), qb = zero2(), qc = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) {
+                const f2 *qrow = sQ + (r + ky) * T::Q_PITCH + 2 * k;
+                const float4 ab = *reinterpret_cast<const float4 *>(qrow);
+                const f2 c = qrow[2];
+                qa = make_float2(fmaxf(qa.x, ab.x), fmaxf(qa.y, ab.y));
+                qb = make_float2(fmaxf(qb.x, ab.z), fmaxf(qb.y, ab.w));
+                qc = make_float2(fmaxf(qc.x, c.x), fmaxf(qc.y, c.y));
+            }
+            const float thr = P.quick_thr;
+            float lo = fminf(fminf(qa.x, qa.y), fminf(qb.x, qb.y));
+            if (kPX * k + 4 <= TW) lo = fminf(lo, fminf(qc.x, qc.y));   // columns 8k+4.. are needed only if inside tile + 1
+            if (lo >= thr) {
+                if (P.reg_value != 1.0f) {   // d = c * reg_value; with the reference's value of 1 the planes already hold d
+                    const f2 gain = make_float2(P.reg_value, P.reg_value);
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) {
+                        float4 *cd = reinterpret_cast<float4 *>(sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k);
+#pragma unroll
+                        for (int q = 0; q < kPX / 2; ++q) {
+                            const float4 tq = cd[q];
+                            const f2 a = mul2(make_float2(tq.x, tq.y), gain), b = mul2(make_float2(tq.z, tq.w), gain);
+                            cd[q] = make_float4(a.x, a.y, b.x, b.y);
+                        }
+                    }
+                }
+                continue;
+            }
         }
         f2 m[kPX];
 #pragma unroll
@@ -766,21 +894,51 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     const bool active = tid < TH * T::E_RUNS && gy < h && gx0 < w;
     f2 acc[kPX][3];
     if (active) {
-#pragma unroll
-        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
+        if constexpr (OWNOTH) {
+            // per input channel: own = its kernel into its own output channel, oth = the ONE kernel it feeds both other
+            // output channels with; e_co = (t_0 + t_1) + t_2 with t_ci = (ci == co ? own_ci : oth_ci)
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
-                f2 v[10];
-                load_cols<5>(sCD + ci * T::CD_PLANE + (r5 + ky) * T::CD_PITCH + kPX * k5, v);
+                f2 own[kPX], oth[kPX];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx)
+                for (int p = 0; p < kPX; ++p) own[p] = oth[p] = zero2();
 #pragma unroll
-                    for (int p = 0; p < kPX; ++p)
+                for (int ky = 0; ky < 3; ++ky) {
+                    f2 v[10];
+                    load_cols<5>(sCD + ci * T::CD_PLANE + (r5 + ky) * T::CD_PITCH + kPX * k5, v);
 #pragma unroll
-                        for (int co = 0; co < 3; ++co)
-                            acc[p][co] = fma2(P.w5[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kPX; ++p) {
+                            own[p] = fma2(P.w5[ky * 3 + kx][ci][0], v[p + kx], own[p]);
+                            oth[p] = fma2(P.w5[ky * 3 + kx][ci][1], v[p + kx], oth[p]);
+                        }
+                }
+#pragma unroll
+                for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) {
+                        const f2 t = co == ci ? own[p] : oth[p];
+                        acc[p][co] = ci == 0 ? t : add2(acc[p][co], t);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    f2 v[10];
+                    load_cols<5>(sCD + ci * T::CD_PLANE + (r5 + ky) * T::CD_PITCH + kPX * k5, v);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kPX; ++p)
+#pragma unroll
+                            for (int co = 0; co < 3; ++co)
+                                acc[p][co] = fma2(P.w5[ky * 3 + kx][ci][co], v[p + kx], acc[p][co]);
+                }
             }
         }
     }
@@ -849,6 +1007,14 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             }
         }
     }
+    if (tilemax && tid < (TH * T::E_RUNS + 31) / 32 * 32) {   // maximum of gray over the whole tile (emit skips most tiles)
+        const int m0 = __reduce_max_sync(0xffffffffu, active ? best0 : 0);
+        const int m1 = __reduce_max_sync(0xffffffffu, active ? best1 : 0);
+        if ((tid & 31) == 0) {
+            if (m0) atomicMax(&sWin[8], m0);
+            if (m1) atomicMax(&sWin[9], m1);
+        }
+    }
     if (P.win.count && tid < (TH * T::E_RUNS + 31) / 32 * 32) {   // whole warps: the reduction needs every lane
         // lanes of a warp hold consecutive rows of one run: reduce per window across the warp (0 is the identity and
         // what inactive lanes carry), then one shared atomic per warp instead of one 32-way serialised atomic
@@ -897,6 +1063,11 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
                 atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], sWin[tid]);
         }
     }
+    if (tilemax && tid >= 32 && tid < 34) {   // [image][tile row][tile column], ordered-int encoding like winmax
+        const int lane = tid - 32;
+        if (lane == 0 || has_b)
+            tilemax[((size_t)(lane ? img1 : img0) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sWin[8 + lane];
+    }
     if (issued_line_end) bulk_wait_read();   // the CTA's shared memory must outlive the reads
 }
 
@@ -939,6 +1110,8 @@ struct StackPlanHost {
     ParamsA a;
     ParamsB b;
     bool s1_depthwise, s2_rgby;
+    bool s2_shared;           // rgby_3's shared-surround structure (stack_a_kernel, S2 mode 2)
+    bool s3_sym, s5_ownoth;   // structure of the stripe / end filters (see stack_b_kernel)
 };
 
 // Validate the structure the fused kernels rely on and repack the HWIO filters as (w, w) pairs.
@@ -961,13 +1134,59 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
                                                     "stack needs identical input slices (use the per-operator calls)", t);
                 S->b.w3[t][co] = dup(W->stripe[(t * 3) * 3 + co]);
             }
+    {   // rgby_3 shared-surround structure (all comparisons bitwise; 2 * S is exact in float32)
+        const float *R = W->rgby;
+        auto at = [&](int t, int ci, int co) { return R[(t * 3 + ci) * 3 + co]; };
+        bool ok = bits_equal(at(4, 0, 1), 0.0f);
+        for (int t = 0; t < 9 && ok; ++t) {
+            const float sv = at(t, 0, 1);
+            ok = bits_equal(at(t, 0, 2), sv) && bits_equal(at(t, 1, 0), sv) && bits_equal(at(t, 2, 0), sv);
+            if (t != 4)
+                ok = ok && bits_equal(at(t, 1, 2), 2.0f * sv) && bits_equal(at(t, 2, 1), 2.0f * sv) &&
+                     bits_equal(at(t, 0, 0), 0.0f) && bits_equal(at(t, 1, 1), 0.0f) && bits_equal(at(t, 2, 2), 0.0f);
+            S->a.s2s[t] = dup(sv);
+        }
+        S->s2_shared = ok && S->s2_rgby;
+        S->a.s2c[0] = dup(at(4, 0, 0)), S->a.s2c[1] = dup(at(4, 1, 1)), S->a.s2c[2] = dup(at(4, 2, 2));
+        S->a.s2c[3] = dup(at(4, 1, 2)), S->a.s2c[4] = dup(at(4, 2, 1)), S->a.s2c[5] = dup(2.0f);
+    }
+    float blur_min = INFINITY;
     for (int t = 0; t < 49; ++t) {
         for (int s = 0; s < 9; ++s)
             if (!bits_equal(W->blur[t * 9 + s], W->blur[t * 9]))
                 return fail(SILENT_E_STRUCTURE, "blur filter slices differ at tap %d; the fused stack needs one 7x7 "
                                                 "kernel in every slice (use the per-operator calls)", t);
         S->b.wb[t] = dup(W->blur[t * 9]);
+        blur_min = W->blur[t * 9] < blur_min ? W->blur[t * 9] : blur_min;   // (a NaN weight leaves blur_min alone ...)
+        if (!(W->blur[t * 9] > 0.0f) || std::isinf(W->blur[t * 9])) blur_min = -1.0f;   // ... and lands here
     }
+    // S4 early-out threshold: the smallest float T with rn(w_min * T) >= 1 (only when every blur weight is positive)
+    S->b.quick_thr = 0.0f;
+    if (blur_min > 0.0f && blur_min < INFINITY) {
+        float T = 1.0f / blur_min;
+        for (int guard = 0; guard < 8 && !(blur_min * T >= 1.0f); ++guard) T = std::nextafterf(T, INFINITY);
+        if (blur_min * T >= 1.0f && T < 1.0e30f) S->b.quick_thr = T;
+    }
+    // stripe kernels symmetric under a 180-degree rotation: w3[0..4] already are the five distinct taps
+    S->s3_sym = true;
+    for (int t = 0; t < 4; ++t)
+        for (int co = 0; co < 3; ++co)
+            if (!bits_equal(W->stripe[(t * 3) * 3 + co], W->stripe[((8 - t) * 3) * 3 + co])) S->s3_sym = false;
+    // end filter: input channel ci feeds both other output channels with the same kernel
+    S->s5_ownoth = true;
+    for (int t = 0; t < 9; ++t)
+        for (int ci = 0; ci < 3; ++ci) {
+            const int o1 = (ci + 1) % 3, o2 = (ci + 2) % 3;
+            if (!bits_equal(W->end[(t * 3 + ci) * 3 + o1], W->end[(t * 3 + ci) * 3 + o2])) S->s5_ownoth = false;
+        }
+    if (!(S->s3_sym && S->s5_ownoth)) S->s3_sym = S->s5_ownoth = false;   // two kernel variants: structured or dense
+    if (S->s5_ownoth)
+        for (int t = 0; t < 9; ++t)
+            for (int ci = 0; ci < 3; ++ci) {
+                S->b.w5[t][ci][0] = dup(W->end[(t * 3 + ci) * 3 + ci]);
+                S->b.w5[t][ci][1] = dup(W->end[(t * 3 + ci) * 3 + (ci + 1) % 3]);
+                S->b.w5[t][ci][2] = dup(0.0f);
+            }
     S->a.h = S->b.h = h;
     S->a.w = S->b.w = w;
     S->a.n = S->b.n = n;
@@ -994,7 +1213,7 @@ struct ThreadsB {
     static constexpr int value = ((TH + 8) * TileB<TH, TW>::C_RUNS + 31) / 32 * 32;
 };
 
-template <int TW, bool DW, bool RGBY, bool PAIRED>
+template <int TW, bool DW, int RGBY, bool PAIRED>
 static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, int pairs, cudaStream_t stream)
 {
     using T = TileA<kTileHA, TW>;
@@ -1010,31 +1229,31 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
 // room for one float2 plane per image pair (n images pair up into at most (n + levels) / 2 pairs for any pairing)
 size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 256; }
 
+// three variants: the reference's filters (depthwise rgc + shared-surround rgby), their zero patterns only, dense
 template <int TW, bool PAIRED>
-static int dispatch_a(bool dw, bool rgby, const void *in, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, int pairs,
-                      cudaStream_t stream)
+static int dispatch_a(bool dw, bool rgby, bool shared, const void *in, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2,
+                      int pairs, cudaStream_t stream)
 {
-    if (dw && rgby) return launch_a<TW, true, true, PAIRED>(in, P, tmap, bsum2, pairs, stream);
-    if (dw) return launch_a<TW, true, false, PAIRED>(in, P, tmap, bsum2, pairs, stream);
-    if (rgby) return launch_a<TW, false, true, PAIRED>(in, P, tmap, bsum2, pairs, stream);
-    return launch_a<TW, false, false, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    if (dw && shared) return launch_a<TW, true, 2, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    if (dw && rgby) return launch_a<TW, true, 1, PAIRED>(in, P, tmap, bsum2, pairs, stream);
+    return launch_a<TW, false, 0, PAIRED>(in, P, tmap, bsum2, pairs, stream);
 }
 
-template <int TH, int TW>
+template <int TH, int TW, bool STRUCTURED>
 static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float *line_end, float *gray, int *winmax,
-                    cudaStream_t stream)
+                    int *tilemax, cudaStream_t stream)
 {
     const int h = S.b.h, w = S.b.w;
     CUtensorMap map_b;
     std::memset(&map_b, 0, sizeof(map_b));
     using TB = TileB<TH, TW>;
     constexpr int NT = ThreadsB<TH, TW>::value;
-    auto kern = stack_b_kernel<TH, TW, NT>;
+    auto kern = stack_b_kernel<TH, TW, NT, STRUCTURED, STRUCTURED>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
     S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
     const dim3 grid(ceil_div(w, TW), ceil_div(h, TH), pairs);
     SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, orient, line_end, gray,
-                                 winmax));
+                                 winmax, tilemax));
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
@@ -1048,18 +1267,30 @@ static int launch_stack_a(const void *pyr, StackPlanHost &S, bool paired_in, int
     using TA = TileA<kTileHA, TWA>;
     S.a.prefetch_pairs = 8;   // ~ the image pairs whose tiles are resident on the chip at once
     S.a.use_tma = paired_in && make_pair_map(&map_x, pyr, w, h, 3LL * pairs, TA::X_PITCH, TA::X_ROWS, 3);
-    return paired_in ? dispatch_a<TWA, true>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream)
-                     : dispatch_a<TWA, false>(S.s1_depthwise, S.s2_rgby, pyr, S.a, map_x, bsum2, pairs, stream);
+    return paired_in ? dispatch_a<TWA, true>(S.s1_depthwise, S.s2_rgby, S.s2_shared, pyr, S.a, map_x, bsum2, pairs, stream)
+                     : dispatch_a<TWA, false>(S.s1_depthwise, S.s2_rgby, S.s2_shared, pyr, S.a, map_x, bsum2, pairs, stream);
 }
 
 template <int TW>
 static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int pairs, f2 *bsum2, float *orient,
-                        float *line_end, float *gray, int *winmax, cudaStream_t stream, cudaEvent_t between_kernels)
+                        float *line_end, float *gray, int *winmax, int *tilemax, cudaStream_t stream,
+                        cudaEvent_t between_kernels)
 {
     int rc = launch_stack_a<TW>(pyr, S, paired_in, pairs, bsum2, stream);   // (96-wide stack_a tiles: measured 8 % slower)
     if (rc != SILENT_OK) return rc;
     if (between_kernels) SILENT_CUDA(cudaEventRecord(between_kernels, stream));   // stage timing hook
-    return launch_b<kTileHB, TW>(S, pairs, bsum2, orient, line_end, gray, winmax, stream);
+    if (S.s3_sym && S.s5_ownoth)
+        return launch_b<kTileHB, TW, true>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream);
+    return launch_b<kTileHB, TW, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream);
+}
+
+// Tile grid of stack_b for a level shape (the emit stage reads the per-tile maxima it writes).
+void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx)
+{
+    *tile_h = kTileHB;
+    *tile_w = pick_tile_w(w);
+    *nty = ceil_div(h, *tile_h);
+    *ntx = ceil_div(w, *tile_w);
 }
 
 // pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
@@ -1067,7 +1298,7 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
 // winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
-                int *winmax, cudaStream_t stream, cudaEvent_t between_kernels)
+                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels)
 {
     if (!pyr) return fail(SILENT_E_INVAL, "silent_stack_fused: null pyramid");
     if (n <= 0 || h <= 0 || w <= 0) return fail(SILENT_E_INVAL, "silent_stack_fused: bad shape %dx%dx%d", n, h, w);
@@ -1088,8 +1319,10 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     S.a.pair_levels = S.b.pair_levels = levels;
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     if (pick_tile_w(w) == 48)
-        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, stream, between_kernels);
-    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, stream, between_kernels);
+        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream,
+                                between_kernels);
+    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream,
+                            between_kernels);
 }
 
 }  // namespace silent
@@ -1107,7 +1340,7 @@ int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const sile
                        size_t workspace_bytes, silent_stream stream)
 {
     return silent::stack_fused(pyramid_dev, n, h, w, 0, weights_host, orient_dev, line_end_dev, gray_dev, workspace_dev,
-                               workspace_bytes, nullptr, nullptr, (cudaStream_t)stream);
+                               workspace_bytes, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -52,16 +52,42 @@ def test_stack_oracle_equals_reference_code_on_shim(goldens, default_filters):
     assert len(S["flat_points"]) < len(S["noise_points"])
 
 
-def test_c_oracle_against_literal(goldens, default_filters, c_oracle):
+@pytest.mark.parametrize("order", ["fused", "operator"])
+def test_c_oracle_against_literal(goldens, default_filters, c_oracle, order):
+    """Both canonical orders of the bit-defined oracle against the reference's own code run on the shim."""
     S = goldens["stack"]
     for name in ("noise", "noise_odd", "natural", "flat"):
         pyr = S[name + "_pyramid"]
-        r = c_oracle.line_end_stack(pyr, default_filters)
+        r = c_oracle.line_end_stack(pyr, default_filters, order=order)
         for key in ("rgc", "rgby", "orient", "line_end", "padded", "gray"):
             a, b = r[key], S[name + "_" + key]
             assert np.array_equal(np.isnan(a), np.isnan(b)), (name, key)
             assert np.nanmax(np.abs(a - b)) <= 1e-5 * np.nanmax(np.abs(b)), (name, key)
         assert np.array_equal(r["points"], S[name + "_points"]), name
+
+
+def test_c_oracle_fused_order_uses_the_structures(default_filters, c_oracle):
+    """The reference's generators produce the structures the fused order relies on; perturbed filters fall back to the
+    operator order bit for bit."""
+    L = c_oracle.lib()
+    W = {k: np.ascontiguousarray(v, np.float32) for k, v in default_filters.items()}
+    assert L.so_depthwise3(W["rgc"]) and L.so_rgby_shared(W["rgby"]) and L.so_stripe_sym180(W["stripe"])
+    assert L.so_end_ownoth(W["end"])
+    pyr = np.random.RandomState(5).rand(2, 20, 28, 3).astype(np.float32) * 255
+    fused = c_oracle.line_end_stack(pyr, default_filters)
+    oper = c_oracle.line_end_stack(pyr, default_filters, order="operator")
+    assert not np.array_equal(fused["orient"], oper["orient"])           # a different rounding order ...
+    assert np.abs(fused["orient"] - oper["orient"]).max() <= 1e-5 * oper["orient"].max()   # ... of the same math
+    broken = dict(default_filters)
+    broken["rgby"] = np.array(default_filters["rgby"], copy=True)
+    broken["rgby"][0, 0, 1, 2] *= 1.5
+    broken["end"] = np.array(default_filters["end"], copy=True)
+    broken["end"][2, 1, 0, 1] += 0.01
+    Wb = {k: np.ascontiguousarray(v, np.float32) for k, v in broken.items()}
+    assert not L.so_rgby_shared(Wb["rgby"]) and not L.so_end_ownoth(Wb["end"])
+    a, b = c_oracle.line_end_stack(pyr, broken), c_oracle.line_end_stack(pyr, broken, order="operator")
+    for key in ("orient", "padded", "gray"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
 
 
 def test_c_oracle_pyramid_against_goldens(goldens, c_oracle):
