@@ -188,7 +188,13 @@ int silent_pack_points(const int64_t *points_dev, const int64_t *count_dev, int6
  * orient_dev (orient_tensor), line_end_dev (padded_line_end_tensor), both [n,h,w,3], and gray_dev [n,h,w,1]
  * (gray_line_end_tensor). Any output pointer may be NULL to skip its store. Returns SILENT_E_STRUCTURE when the weights
  * are not (stripe: identical input-channel slices; blur: all slices identical), which the reference's generators
- * always produce. */
+ * always produce.
+ * PRECONDITION: every input value is finite with magnitude <= 1e30. The fused kernels skip exact-zero weights, share
+ * sub-kernels between output channels (rgby_3's surround, the end filter's "other channel" kernel, the stripe filter's
+ * point symmetry -- each detected bitwise on the weights) and leave the 7x7 blur out where it is provably >= 1; all of
+ * that is exact for finite data, but NaN / Inf inputs would not propagate the way the reference graph propagates them
+ * (0 * inf = NaN). Callers with such data use the per-operator entry points (silent_conv2d, silent_regulate, ...), as
+ * LineEndPipeline.run does. uint8 frames (silent_pipeline_run*) always satisfy the precondition. */
 size_t silent_stack_workspace_bytes(int n, int h, int w);
 int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const silent_stack_weights *weights_host,
                        float *orient_dev, float *line_end_dev, float *gray_dev, void *workspace_dev,

@@ -20,6 +20,11 @@ def _require_cuda():
         raise RuntimeError("pysilent_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
 
 
+# largest input magnitude the fused stack accepts: no stage can overflow to Inf from here (the five filters together
+# amplify by well under 1e6), so every intermediate of the fused kernels stays finite until the regulator's own 0 * inf
+FUSED_INPUT_MAX = 1.0e30
+
+
 def as_device_tensor(t, dtype=torch.float32):
     """torch CUDA / numpy -> contiguous CUDA tensor of ``dtype``."""
     _require_cuda()

@@ -70,12 +70,8 @@ __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict
 
 // One warp per row (level, y). Pass 0 counts hits, pass 1 writes them at row_offset in x order.
 // COUNT pass: one warp per row (level, y); 128-bit loads when the row length allows; writes the row's hit count.
-// With the per-tile maxima that stack_b_kernel leaves behind, a row first asks whether ANY of its tiles can hold a hit
-// (tile maximum >= the smallest region maximum the tile is compared with); on generic input a handful of tiles per level
-// can, so almost every row returns without touching `value` at all.
 __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict__ value, int rows, int h, int w, PoolGeom g,
-                                                         const float *__restrict__ pooled, int *__restrict__ row_count,
-                                                         TileMaxima tm)
+                                                         const float *__restrict__ pooled, int *__restrict__ row_count)
 {
     pdl_enter();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -84,26 +80,6 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const float *__restrict
     const int n = row / h, y = row - n * h;
     const float *v = value + (size_t)row * w;
     const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
-    if (tm.data) {
-        const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
-        bool any = false;
-        for (int t0 = 0; t0 < tm.ntx; t0 += 32) {
-            const int tx = t0 + lane;
-            bool cand = false;
-            if (tx < tm.ntx) {
-                const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w) - 1;
-                const int best = __ldg(tile_row + tx);
-                cand = best == 0x7fc00000;   // a NaN somewhere in the tile: let the exact pass decide
-                const float bf = __int_as_float(best);
-                for (int j = nearest_src(x0, g.sx, g.ow); j <= nearest_src(x1, g.sx, g.ow); ++j) cand |= bf >= __ldg(pool_row + j);
-            }
-            any |= __any_sync(0xffffffffu, cand);
-        }
-        if (!any) {
-            if (lane == 0) row_count[row] = 0;
-            return;
-        }
-    }
     int hits = 0;
     if ((w & 3) == 0) {
         for (int q = lane; q < (w >> 2); q += 32) {
@@ -192,6 +168,122 @@ __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict
             }
         }
         base += __popc(ballot);
+    }
+}
+
+// ---- fused path: per-tile maxima are available (stack_b_kernel), so a level is ONE CTA --------------------------------
+// A thread owns a row. It looks at the tiles its row crosses and scans only those whose maximum can reach the region
+// maximum it is compared with (a handful of tiles per level on generic input; every tile of an all-zero level).
+// emit_count_kernel: hit count per row -> exclusive scan inside the CTA -> row offsets + level total.
+// emit_write_kernel: sum of the totals of the levels before this one, then the rows with hits write their points in x
+// order: the int64 rows (level, y, x, 0) come out in tf.where's row-major order. Two launches of n small CTAs instead of
+// three launches of n * h / 8.
+__device__ __forceinline__ bool tile_is_candidate(const TileMaxima &tm, const int *__restrict__ tile_row, int tx, int w,
+                                                  const PoolGeom &g, const float *__restrict__ pool_row)
+{
+    const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w) - 1;
+    const int best = __ldg(tile_row + tx);
+    bool cand = best == 0x7fc00000;   // a NaN somewhere in the tile: let the exact comparison decide
+    const float bf = __int_as_float(best);
+    for (int j = nearest_src(x0, g.sx, g.ow); j <= nearest_src(x1, g.sx, g.ow); ++j) cand |= bf >= __ldg(pool_row + j);
+    return cand;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ int scan_row_tiles(const float *__restrict__ v, int n, int y, int w, const PoolGeom &g,
+                                              const float *__restrict__ pool_row, const TileMaxima &tm,
+                                              const int *__restrict__ tile_row, long long *__restrict__ points,
+                                              long long slot, long long capacity)
+{
+    int hits = 0;
+    for (int tx = 0; tx < tm.ntx; ++tx) {
+        if (!tile_is_candidate(tm, tile_row, tx, w, g, pool_row)) continue;
+        const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w);
+        for (int x = x0; x < x1; ++x) {
+            if (__ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow))) {
+                if (WRITE && slot + hits < capacity) {
+                    reinterpret_cast<longlong2 *>(points)[(slot + hits) * 2] = make_longlong2(n, y);
+                    reinterpret_cast<longlong2 *>(points)[(slot + hits) * 2 + 1] = make_longlong2(x, 0);
+                }
+                ++hits;
+            }
+        }
+    }
+    return hits;
+}
+
+__global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
+                                                         const float *__restrict__ pooled, TileMaxima tm,
+                                                         int *__restrict__ row_offset, int *__restrict__ level_total)
+{
+    pdl_enter();
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < h; base += 256) {
+        const int y = base + threadIdx.x;
+        int mine = 0;
+        if (y < h) {
+            const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
+            const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
+            mine = scan_row_tiles<false>(value + ((size_t)n * h + y) * w, n, y, w, g, pool_row, tm, tile_row, nullptr, 0, 0);
+        }
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = s_carry + incl - mine;
+        for (int k = 0; k < warp; ++k) before += s_warp[k];
+        if (y < h) row_offset[(size_t)n * h + y] = before | (mine ? 0x40000000 : 0);   // bit 30: the row has hits
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = before + mine;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) level_total[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
+                                                         const float *__restrict__ pooled, TileMaxima tm,
+                                                         const int *__restrict__ row_offset,
+                                                         const int *__restrict__ level_total, int levels,
+                                                         long long *__restrict__ points, long long capacity,
+                                                         long long *__restrict__ total)
+{
+    pdl_enter();
+    __shared__ long long s_sum[8];
+    __shared__ int s_any;
+    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool last = n == levels - 1;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    // does this level write anything at all? (most CTAs leave here)
+    int any = 0;
+    for (int y = threadIdx.x; y < h; y += 256) any |= __ldg(row_offset + (size_t)n * h + y) & 0x40000000;
+    if (any) s_any = 1;
+    __syncthreads();
+    if (!(s_any && capacity > 0) && !last) return;
+    // points of the levels before this one (the last level also publishes the grand total)
+    long long sum = 0;
+    for (int k = threadIdx.x; k < n; k += 256) sum += __ldg(level_total + k);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_sum[warp] = sum;
+    __syncthreads();
+    long long before = 0;
+    for (int k = 0; k < 8; ++k) before += s_sum[k];
+    if (last && threadIdx.x == 0) *total = before + __ldg(level_total + n);
+    if (!s_any || capacity <= 0) return;
+    for (int y = threadIdx.x; y < h; y += 256) {
+        const int packed = __ldg(row_offset + (size_t)n * h + y);
+        if (!(packed & 0x40000000)) continue;
+        const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
+        const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
+        scan_row_tiles<true>(value + ((size_t)n * h + y) * w, n, y, w, g, pool_row, tm, tile_row, points,
+                             before + (packed & 0x3fffffff), capacity);
     }
 }
 
@@ -301,9 +393,19 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
         SILENT_LAUNCH_CHECK("window_max_kernel");
     }
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
+    if (tiles && tiles->data) {   // fused path: one CTA per level, rows skip the tiles that cannot hold a hit
+        SILENT_CUDA(launch_dependent(emit_count_kernel, dim3(n), dim3(256), 0, stream, value, h, w, g, (const float *)pooled,
+                                     *tiles, row_offset, level_total));
+        SILENT_LAUNCH_CHECK("emit_count_kernel");
+        SILENT_CUDA(launch_dependent(emit_write_kernel, dim3(n), dim3(256), 0, stream, value, h, w, g, (const float *)pooled,
+                                     *tiles, (const int *)row_offset, (const int *)level_total, n, (long long *)points,
+                                     (long long)capacity, (long long *)count));
+        SILENT_LAUNCH_CHECK("emit_write_kernel");
+        return SILENT_OK;
+    }
     const unsigned blocks = (unsigned)ceil_div(rows, 8);
     SILENT_CUDA(launch_dependent(count_rows_kernel, dim3(blocks), dim3(256), 0, stream, value, rows, h, w, g,
-                                 (const float *)pooled, row_offset, tiles ? *tiles : TileMaxima()));
+                                 (const float *)pooled, row_offset));
     SILENT_LAUNCH_CHECK("count_rows_kernel");
     SILENT_CUDA(launch_dependent(scan_level_kernel, dim3(n), dim3(256), 0, stream, row_offset, h, level_total));
     SILENT_LAUNCH_CHECK("scan_level_kernel");

@@ -38,7 +38,7 @@ static void release(Workspace &ws)
 
 // Page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory) can be copied asynchronously in place;
 // pageable memory is staged through the plan's pinned mirrors.
-static bool is_pinned(const void *p)
+static bool is_pinned_at(const void *p)
 {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
@@ -46,6 +46,11 @@ static bool is_pinned(const void *p)
         return false;
     }
     return attr.type == cudaMemoryTypeHost;
+}
+// both ends of the range: a buffer that only STARTS in a page-locked allocation is staged like pageable memory
+static bool is_pinned(const void *p, size_t bytes)
+{
+    return p && bytes > 0 && is_pinned_at(p) && is_pinned_at((const char *)p + bytes - 1);
 }
 
 static size_t frame_bytes(const silent_plan *plan)
@@ -262,9 +267,9 @@ int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weig
         if (!ws.ev_in[i]) SILENT_CUDA(cudaEventCreateWithFlags(&ws.ev_in[i], cudaEventDisableTiming));
         if (!ws.ev_done[i]) SILENT_CUDA(cudaEventCreateWithFlags(&ws.ev_done[i], cudaEventDisableTiming));
     }
-    const bool frames_direct = is_pinned(frames_host);
-    const bool orient_direct = orient_host && is_pinned(orient_host);
-    const bool line_end_direct = line_end_host && is_pinned(line_end_host);
+    const bool frames_direct = is_pinned(frames_host, fbytes * batch);
+    const bool orient_direct = orient_host && is_pinned(orient_host, n * image_bytes);
+    const bool line_end_direct = line_end_host && is_pinned(line_end_host, n * image_bytes);
     if (!frames_direct && !ws.h_frames) SILENT_CUDA(cudaMallocHost(&ws.h_frames, fbytes * ws.batch));
     if (orient_host && !orient_direct && !ws.h_orient) SILENT_CUDA(cudaMallocHost(&ws.h_orient, cap_tensor_bytes));
     if (line_end_host && !line_end_direct && !ws.h_line_end)
@@ -279,48 +284,65 @@ int silent_pipeline_run_host(silent_plan *plan, const silent_stack_weights *weig
     SILENT_CUDA(cudaStreamWaitEvent(ws.s_in, ws.ev_done[0], 0));
     SILENT_CUDA(cudaStreamWaitEvent(ws.s_out, ws.ev_done[0], 0));
     if (fuse_windows) SILENT_CUDA(cudaMemsetAsync(ws.d_winmax, 0, n * geo.count * sizeof(int), s));
-    const int per = host_chunk_frames(batch);
-    int chunk = 0;
-    for (int f0 = 0; f0 < batch; f0 += per, ++chunk) {
-        const int nb = std::min(per, batch - f0);
-        const char *src = (const char *)frames_host + fbytes * f0;
-        if (!frames_direct) {
-            std::memcpy((char *)ws.h_frames + fbytes * f0, src, fbytes * nb);
-            src = (const char *)ws.h_frames + fbytes * f0;
-        }
-        SILENT_CUDA(cudaMemcpyAsync((char *)ws.d_frames + fbytes * f0, src, fbytes * nb, cudaMemcpyHostToDevice, ws.s_in));
-        SILENT_CUDA(cudaEventRecord(ws.ev_in[chunk], ws.s_in));
-        SILENT_CUDA(cudaStreamWaitEvent(s, ws.ev_in[chunk], 0));
-        rc = run_stack_stages(plan, weights_host, ws.d_frames, f0, nb, nullptr, orient_host ? ws.d_orient : nullptr,
-                              line_end_host ? ws.d_line_end : nullptr, fuse_windows ? &geo : nullptr, s);
-        if (rc != SILENT_OK) break;
-        SILENT_CUDA(cudaEventRecord(ws.ev_done[chunk], s));
-        SILENT_CUDA(cudaStreamWaitEvent(ws.s_out, ws.ev_done[chunk], 0));
-        const size_t off = (size_t)f0 * plan->levels * image_bytes, bytes = (size_t)nb * plan->levels * image_bytes;
-        if (orient_host)
-            SILENT_CUDA(cudaMemcpyAsync(orient_dst + off, (char *)ws.d_orient + off, bytes, cudaMemcpyDeviceToHost, ws.s_out));
-        if (line_end_host)
-            SILENT_CUDA(cudaMemcpyAsync(line_end_dst + off, (char *)ws.d_line_end + off, bytes, cudaMemcpyDeviceToHost,
-                                        ws.s_out));
-    }
-    if (rc != SILENT_OK) {   // drain what was queued before reporting the failure
+    // Everything below queues asynchronous work against the caller's buffers and the plan's staging buffers: whatever
+    // goes wrong, ALL three queues are drained before the call returns (run_chunks never returns early past a copy).
+    auto drain = [&]() {
         cudaStreamSynchronize(ws.s_in);
         cudaStreamSynchronize(s);
         cudaStreamSynchronize(ws.s_out);
-        return rc;
+    };
+    if (points_host && capacity > ws.points_capacity) {   // a caller retrying after *count_host > capacity (an all-zero
+        cudaFree(ws.d_points);                             // level emits every pixel): grow the plan's point buffers
+        cudaFreeHost(ws.h_points);
+        ws.d_points = nullptr, ws.h_points = nullptr, ws.points_capacity = 0;
+        SILENT_CUDA(cudaMalloc(&ws.d_points, capacity * 4 * sizeof(int64_t)));
+        SILENT_CUDA(cudaMallocHost(&ws.h_points, capacity * 4 * sizeof(int64_t)));
+        ws.points_capacity = capacity;
     }
     const int64_t cap = capacity < ws.points_capacity ? capacity : ws.points_capacity;
-    const TileMaxima tm = tile_maxima(plan);
-    rc = max_value_indices_region(ws.d_gray, (int)n, plan->h, plan->w, plan->h / 2, plan->w / 2, ws.d_points, cap,
-                                  ws.d_count, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, &tm, s);
-    if (rc == SILENT_OK) {
+    auto run_chunks = [&]() -> int {
+        const int per = host_chunk_frames(batch);
+        int chunk = 0;
+        for (int f0 = 0; f0 < batch; f0 += per, ++chunk) {
+            const int nb = std::min(per, batch - f0);
+            const char *src = (const char *)frames_host + fbytes * f0;
+            if (!frames_direct) {
+                std::memcpy((char *)ws.h_frames + fbytes * f0, src, fbytes * nb);
+                src = (const char *)ws.h_frames + fbytes * f0;
+            }
+            SILENT_CUDA(cudaMemcpyAsync((char *)ws.d_frames + fbytes * f0, src, fbytes * nb, cudaMemcpyHostToDevice, ws.s_in));
+            SILENT_CUDA(cudaEventRecord(ws.ev_in[chunk], ws.s_in));
+            SILENT_CUDA(cudaStreamWaitEvent(s, ws.ev_in[chunk], 0));
+            const int rcs = run_stack_stages(plan, weights_host, ws.d_frames, f0, nb, nullptr,
+                                             orient_host ? ws.d_orient : nullptr, line_end_host ? ws.d_line_end : nullptr,
+                                             fuse_windows ? &geo : nullptr, s);
+            if (rcs != SILENT_OK) return rcs;
+            SILENT_CUDA(cudaEventRecord(ws.ev_done[chunk], s));
+            SILENT_CUDA(cudaStreamWaitEvent(ws.s_out, ws.ev_done[chunk], 0));
+            const size_t off = (size_t)f0 * plan->levels * image_bytes, bytes = (size_t)nb * plan->levels * image_bytes;
+            if (orient_host)
+                SILENT_CUDA(cudaMemcpyAsync(orient_dst + off, (char *)ws.d_orient + off, bytes, cudaMemcpyDeviceToHost, ws.s_out));
+            if (line_end_host)
+                SILENT_CUDA(cudaMemcpyAsync(line_end_dst + off, (char *)ws.d_line_end + off, bytes, cudaMemcpyDeviceToHost,
+                                            ws.s_out));
+        }
+        const TileMaxima tm = tile_maxima(plan);
+        const int rce = max_value_indices_region(ws.d_gray, (int)n, plan->h, plan->w, plan->h / 2, plan->w / 2, ws.d_points,
+                                                 cap, ws.d_count, ws.d_select, ws.select_bytes,
+                                                 fuse_windows ? ws.d_winmax : nullptr, &tm, s);
+        if (rce != SILENT_OK) return rce;
         SILENT_CUDA(cudaMemcpyAsync(ws.h_count, ws.d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
         if (points_host && cap > 0)
             SILENT_CUDA(cudaMemcpyAsync(ws.h_points, ws.d_points, cap * 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    }
-    SILENT_CUDA(cudaStreamSynchronize(s));
-    SILENT_CUDA(cudaStreamSynchronize(ws.s_out));
+        return SILENT_OK;
+    };
+    rc = run_chunks();
+    drain();
     if (rc != SILENT_OK) return rc;
+    {
+        const cudaError_t late = cudaGetLastError();   // an asynchronous failure surfaces at the synchronisation
+        if (late != cudaSuccess) return fail(SILENT_E_CUDA, "silent_pipeline_run_host: %s", cudaGetErrorString(late));
+    }
     const size_t tensor_bytes = n * image_bytes;
     if (orient_host && !orient_direct) std::memcpy(orient_host, ws.h_orient, tensor_bytes);
     if (line_end_host && !line_end_direct) std::memcpy(line_end_host, ws.h_line_end, tensor_bytes);

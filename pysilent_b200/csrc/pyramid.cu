@@ -285,11 +285,9 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     const silent_params &p = plan->params;
     const int pairs = (batch + 1) / 2;
     if (pairs > 65535) return fail(SILENT_E_SHAPE, "at most 131070 frames per call");
-    static bool configured = false;
-    if (!configured) {
-        SILENT_CUDA(cudaFuncSetAttribute(pyramid_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per launch, not once per process: the attribute belongs to the CURRENT device's context, and one process may
+    // drive several GPUs (one LineEndPipeline per camera thread and device)
+    SILENT_CUDA(cudaFuncSetAttribute(pyramid_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PairParams P;
     P.frames = (const uint8_t *)frames_dev;
     P.xpair = (f2 *)xpair_dev;

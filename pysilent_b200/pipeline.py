@@ -96,7 +96,12 @@ class LineEndPipeline:
             return self.run_bank(pyramid_tensor, want_points)
         if self.blur_size != 7:
             return self.run_unfused(pyramid_tensor, want_points)
-        orient, line_end, gray = _ops.stack_fused(pyramid_tensor, self.stack_weights())
+        x = _ops.as_device_tensor(pyramid_tensor)
+        # the fused kernels skip exact-zero weights and shortcut the regulator where the blur is provably >= 1: valid for
+        # finite input only (include/silent_b200.h). NaN / Inf / huge values go operator by operator, like the graph.
+        if not bool((x.abs() <= _ops.FUSED_INPUT_MAX).all()):
+            return self.run_unfused(x, want_points)
+        orient, line_end, gray = _ops.stack_fused(x, self.stack_weights())
         points = None
         if want_points:
             rh, rw = self._region()
@@ -218,7 +223,11 @@ class LineEndPipeline:
                 plan.handle, ctypes.byref(self.stack_weights()), frames.ctypes.data, b, orient_out.ctypes.data,
                 line_end_out.ctypes.data, points.ctypes.data, points_capacity, ctypes.byref(count),
                 _ops.stream_ptr()), "silent_pipeline_run_host")
-        return LineEndResult(orient_out, line_end_out, None, points[:min(count.value, points_capacity)])
+        if count.value > points_capacity:
+            # rare (an all-zero level emits every pixel, top_value_points.py:42-44): redo with room for every point, as
+            # run_frames does -- feature points are never silently truncated
+            return self.run_host(frames, orient_out, line_end_out, points_capacity=int(count.value))
+        return LineEndResult(orient_out, line_end_out, None, points[:count.value])
 
     def callback(self, frame, cam_id=None, depth=2):
         """Per-frame entry point with the reference's signature (``recognition_testing.py:136-144``).

@@ -328,6 +328,80 @@ def test_pipeline_properties_at_full_size(default_filters):
     assert torch.equal(pad_inwards(p, [[0, 0], [2, 2], [2, 2], [0, 0]]), p)
 
 
+@pytest.mark.parametrize("batch", [64, 63])
+def test_pipeline_config3_full_batch_against_oracle(batch, c_oracle, default_filters):
+    """The headline config itself (C3: 1080p, 6 levels, batch 64) against the bit-defined oracle: first, middle and last
+    frames (values, NaN masks, gray-derived points), device-resident and host-buffer entry points; batch 63 leaves a lone
+    frame in the last frame pair."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(3, i, 1080, 1920) for i in range(batch)])
+    pipe = LineEndPipeline(zoom_ratio=2 ** .5)
+    res = pipe.run_frames(torch.from_numpy(frames).cuda())
+    host = pipe.run_host(frames) if batch == 64 else None
+    L = 6
+    assert tuple(res.orient.shape) == (batch * L, 192, 288, 3)
+    pts = res.points.cpu().numpy()
+    for i in (0, 31, batch - 2, batch - 1):
+        pyr, ref = _oracle_pipeline(c_oracle, frames[i:i + 1], (288, 192), 2 ** .5, default_filters)
+        assert pyr.shape[0] == L
+        sl = slice(i * L, (i + 1) * L)
+        assert_bits(res.orient[sl], ref["orient"], "C3 frame %d orient" % i)
+        assert_bits(res.padded_line_end[sl], ref["padded"], "C3 frame %d padded_line_end" % i)
+        sel = pts[(pts[:, 0] >= i * L) & (pts[:, 0] < (i + 1) * L)].copy()
+        sel[:, 0] -= i * L
+        assert np.array_equal(sel, ref["points"]), "C3 frame %d points" % i
+        if host is not None:
+            assert_bits(host.orient[sl], ref["orient"], "C3 host frame %d orient" % i)
+            assert_bits(host.padded_line_end[sl], ref["padded"], "C3 host frame %d padded_line_end" % i)
+    if host is not None:
+        assert np.array_equal(host.points, pts)
+
+
+def test_run_host_returns_every_point():
+    """run_host never truncates the feature points: a too-small capacity is retried with the reported count, and a
+    capacity beyond the plan's own point buffer grows it."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(1, i, 240, 320) for i in range(2)])
+    pipe = LineEndPipeline(output_size=(96, 64), zoom_ratio=1.5)
+    dev = pipe.run_frames(torch.from_numpy(frames).cuda()).points.cpu().numpy()
+    assert len(dev) > 1
+    assert np.array_equal(pipe.run_host(frames, points_capacity=1).points, dev)
+    assert np.array_equal(pipe.run_host(frames, points_capacity=200000).points, dev)
+
+
+def test_two_devices_in_one_process(default_filters):
+    """One process, two GPUs (camera threads on different devices): per-device kernel attributes (the pyramid kernel's
+    dynamic shared memory at 1080p exceeds the 48 KB default) must be set on each device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(2, i, 1080, 1920) for i in range(2)])
+    outs = []
+    for d in (0, 1):
+        pipe = LineEndPipeline(zoom_ratio=2 ** .5, device="cuda:%d" % d)
+        with torch.cuda.device(d):
+            res = pipe.run_frames(torch.from_numpy(frames).to("cuda:%d" % d))
+            outs.append((res.orient.cpu(), res.padded_line_end.cpu(), res.points.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+def test_fused_stack_routes_non_finite_input(c_oracle, default_filters):
+    """``run(pyramid)`` on input with NaN / Inf: the fused kernels assume finite input (they skip exact-zero weights and
+    shortcut the regulator), so the pipeline takes the per-operator path, which propagates like the reference graph."""
+    from pysilent_b200 import LineEndPipeline
+    pyr = _pyr(77, 2, 40, 56)
+    pyr[0, 10, 12, 1] = np.nan
+    pyr[1, 20, 30, 0] = np.inf
+    pipe = LineEndPipeline(output_size=(56, 40))
+    res = pipe.run(pyr)
+    ref = c_oracle.line_end_stack(pyr, default_filters, order="operator")
+    assert np.isnan(ref["orient"]).any()
+    _check_stack(res, ref, None, "non-finite pyramid")
+    clean = _pyr(77, 2, 40, 56)
+    _check_stack(pipe.run(clean), c_oracle.line_end_stack(clean, default_filters), None, "finite pyramid (fused)")
+
+
 # ---- BASELINE config C4: 8-orientation bank, 8-level 4K pyramid ----------------------------------------------------------
 
 def _oracle_bank(c_oracle, pyr, f, region):
@@ -380,6 +454,18 @@ def test_orientation_bank_config4_full_size_properties():
     pts = full.points.cpu().numpy()
     key = (pts[:, 0] * 192 + pts[:, 1]) * 288 + pts[:, 2]
     assert len(pts) > 0 and (np.diff(key) > 0).all()
+
+
+def test_orientation_bank_config4_4k_against_oracle(c_oracle):
+    """C4 at its named frame shape: one 3840x2160 frame, all 8 levels, 8 orientations, against the bit-defined oracle."""
+    from pysilent_b200 import LineEndPipeline
+    frame = synthetic_frame(4, 0, 2160, 3840)
+    pipe = LineEndPipeline(zoom_ratio=2 ** .5, orientations=8)
+    res = pipe.run_frames(torch.from_numpy(frame[None]).cuda())
+    pyr = c_oracle.from_image(frame[None], 3, (288, 192), 2 ** .5)
+    assert pyr.shape == (8, 192, 288, 3)
+    ref = _oracle_bank(c_oracle, pyr, pipe.bank_filters(), (96, 144))
+    _check_stack(res, ref, None, "config 4 at 4K")
 
 
 # ---- BASELINE config C5: many 720p streams; host-buffer entry point from several camera threads --------------------------

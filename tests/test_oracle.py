@@ -190,3 +190,60 @@ def test_recovery_selection_like_reference():
     assert (recovery_mode(False, True), recovery_mode(True, False), recovery_mode(True, True)) == (1, 2, 3)
     with pytest.raises(ValueError):
         recovery_mode(False, False)
+
+
+# ---- the TF-1 stand-in pinned by an independent implementation (torch on CPU) ---------------------------------------------
+
+def _shim():
+    from oracle import tf1_shim
+    return tf1_shim
+
+
+@pytest.mark.parametrize("h,w", [(9, 12), (10, 13), (16, 16), (1, 5)])
+@pytest.mark.parametrize("k", [3, 7, 2, 4])
+def test_shim_conv2d_same_matches_torch(h, w, k):
+    """tf.nn.conv2d(SAME, stride 1) of the shim vs torch.nn.functional.conv2d: cross-correlation, HWIO filters, zero
+    padding with the extra pad row / column at the END for even kernels (TF's pad_before = pad_total // 2)."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    rs = np.random.RandomState(100 * k + h)
+    x = rs.randn(2, h, w, 3).astype(np.float32)
+    wt = rs.randn(k, k, 3, 4).astype(np.float32)
+    got = _shim().conv2d(input=x, filter=wt, strides=[1, 1, 1, 1], padding="SAME").numpy()
+    total = k - 1
+    xp = F.pad(torch.from_numpy(x).permute(0, 3, 1, 2).double(), (total // 2, total - total // 2, total // 2, total - total // 2))
+    want = F.conv2d(xp, torch.from_numpy(wt).permute(3, 2, 0, 1).double()).permute(0, 2, 3, 1).numpy()
+    assert got.shape == want.shape == (2, h, w, 4)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    if k % 2:   # torch's own 'same' padding agrees with TF's for odd kernels
+        same = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), torch.from_numpy(wt).permute(3, 2, 0, 1).double(),
+                        padding="same").permute(0, 2, 3, 1).numpy()
+        assert np.abs(got - same).max() <= 1e-5 * np.abs(same).max()
+
+
+@pytest.mark.parametrize("h,w,rh,rw", [(8, 12, 4, 6), (9, 13, 4, 6), (192, 288, 96, 144), (7, 5, 3, 2), (6, 6, 6, 6)])
+def test_shim_max_pool_whole_level_window_matches_torch(h, w, rh, rw):
+    """max_value_indices_region's pooling (top_value_points.py:39): ksize = the whole level, stride = the region, SAME.
+    torch: explicit -inf padding with TF's pad_before = pad_total // 2, then an unpadded max_pool2d."""
+    torch = pytest.importorskip("torch")
+    F = torch.nn.functional
+    x = np.random.RandomState(h * w).randn(2, h, w, 1).astype(np.float32)
+    got = _shim().max_pool(x, [1, h, w, 1], strides=[1, rh, rw, 1], padding="SAME").numpy()
+    oh, ow = -(-h // rh), -(-w // rw)
+    th, tw = max((oh - 1) * rh + h - h, 0), max((ow - 1) * rw + w - w, 0)
+    xp = F.pad(torch.from_numpy(x).permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2), value=float("-inf"))
+    want = F.max_pool2d(xp, kernel_size=(h, w), stride=(rh, rw)).permute(0, 2, 3, 1).numpy()
+    assert got.shape == want.shape == (2, oh, ow, 1)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(2, 2, 192, 288), (2, 2, 9, 13), (3, 4, 10, 10), (64, 96, 192, 288), (5, 7, 5, 7)])
+def test_shim_resize_nearest_matches_torch(h, w, oh, ow):
+    """tf.image.resize_images(NEAREST, align_corners=False): src = min(floor(dst * in / out), in - 1) -- the rule
+    torch.nn.functional.interpolate(mode='nearest') implements."""
+    torch = pytest.importorskip("torch")
+    x = np.random.RandomState(oh + ow).randn(2, h, w, 3).astype(np.float32)
+    T = _shim()
+    got = T.resize_images(x, [oh, ow], method=T._ResizeMethod.NEAREST_NEIGHBOR).numpy()
+    want = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), size=(oh, ow), mode="nearest")
+    assert np.array_equal(got, want.permute(0, 2, 3, 1).numpy())
