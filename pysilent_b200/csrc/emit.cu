@@ -172,44 +172,27 @@ __global__ void __launch_bounds__(256) write_rows_kernel(const float *__restrict
 }
 
 // ---- fused path: per-tile maxima are available (stack_b_kernel), so a level is ONE CTA --------------------------------
-// A thread owns a row. It looks at the tiles its row crosses and scans only those whose maximum can reach the region
-// maximum it is compared with (a handful of tiles per level on generic input; every tile of an all-zero level).
-// emit_count_kernel: hit count per row -> exclusive scan inside the CTA -> row offsets + level total.
-// emit_write_kernel: sum of the totals of the levels before this one, then the rows with hits write their points in x
-// order: the int64 rows (level, y, x, 0) come out in tf.where's row-major order. Two launches of n small CTAs instead of
-// three launches of n * h / 8.
-__device__ __forceinline__ bool tile_is_candidate(const TileMaxima &tm, const int *__restrict__ tile_row, int tx, int w,
-                                                  const PoolGeom &g, const float *__restrict__ pool_row)
+// Only tiles whose maximum reaches the region maximum they are compared with can hold a hit (a handful per level on
+// generic input; every tile of an all-zero level). emit_count_kernel flags those tiles, scans each flagged tile with the
+// whole CTA (one 128-bit load per thread and round, all independent: a level costs about two memory round trips) and
+// scans the row counts; emit_write_kernel adds up the totals of the levels before its own and lets one warp per row
+// WITH hits write them in x order, so the int64 rows (level, y, x, 0) come out in tf.where's row-major order. Two
+// launches of n CTAs instead of three launches of n * h / 8.
+constexpr int kEmitMaxTiles = 1024;   // tiles per level the one-CTA path handles (else the row kernels run)
+constexpr int kEmitMaxRows = 2048;    // rows per level (shared-memory row counters)
+
+__device__ __forceinline__ bool tile_is_candidate(const TileMaxima &tm, const int *__restrict__ level_tiles, int ty, int tx,
+                                                  int h, int w, const PoolGeom &g, const float *__restrict__ level_pool)
 {
     const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w) - 1;
-    const int best = __ldg(tile_row + tx);
+    const int y0 = ty * tm.tile_h, y1 = min(h, y0 + tm.tile_h) - 1;
+    const int best = __ldg(level_tiles + ty * tm.ntx + tx);
     bool cand = best == 0x7fc00000;   // a NaN somewhere in the tile: let the exact comparison decide
     const float bf = __int_as_float(best);
-    for (int j = nearest_src(x0, g.sx, g.ow); j <= nearest_src(x1, g.sx, g.ow); ++j) cand |= bf >= __ldg(pool_row + j);
+    for (int i = nearest_src(y0, g.sy, g.oh); i <= nearest_src(y1, g.sy, g.oh); ++i)
+        for (int j = nearest_src(x0, g.sx, g.ow); j <= nearest_src(x1, g.sx, g.ow); ++j)
+            cand |= bf >= __ldg(level_pool + i * g.ow + j);
     return cand;
-}
-
-template <bool WRITE>
-__device__ __forceinline__ int scan_row_tiles(const float *__restrict__ v, int n, int y, int w, const PoolGeom &g,
-                                              const float *__restrict__ pool_row, const TileMaxima &tm,
-                                              const int *__restrict__ tile_row, long long *__restrict__ points,
-                                              long long slot, long long capacity)
-{
-    int hits = 0;
-    for (int tx = 0; tx < tm.ntx; ++tx) {
-        if (!tile_is_candidate(tm, tile_row, tx, w, g, pool_row)) continue;
-        const int x0 = tx * tm.tile_w, x1 = min(w, x0 + tm.tile_w);
-        for (int x = x0; x < x1; ++x) {
-            if (__ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow))) {
-                if (WRITE && slot + hits < capacity) {
-                    reinterpret_cast<longlong2 *>(points)[(slot + hits) * 2] = make_longlong2(n, y);
-                    reinterpret_cast<longlong2 *>(points)[(slot + hits) * 2 + 1] = make_longlong2(x, 0);
-                }
-                ++hits;
-            }
-        }
-    }
-    return hits;
 }
 
 __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
@@ -217,19 +200,50 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
                                                          int *__restrict__ row_offset, int *__restrict__ level_total)
 {
     pdl_enter();
+    __shared__ int s_rows[kEmitMaxRows];
+    __shared__ unsigned char s_flag[kEmitMaxTiles];
     __shared__ int s_warp[8];
     __shared__ int s_carry;
-    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *v = value + (size_t)n * h * w;
+    const float *level_pool = pooled + (size_t)n * g.oh * g.ow;
+    const int *level_tiles = tm.data + (size_t)n * tm.nty * tm.ntx;
+    const int ntiles = tm.nty * tm.ntx;
+    for (int y = tid; y < h; y += 256) s_rows[y] = 0;
+    if (tid == 0) s_carry = 0;
+    for (int t = tid; t < ntiles; t += 256)
+        s_flag[t] = tile_is_candidate(tm, level_tiles, t / tm.ntx, t % tm.ntx, h, w, g, level_pool);
+    __syncthreads();
+    const int quads = (tm.tile_w + 3) >> 2;
+    const bool vec_ok = (w & 3) == 0 && (tm.tile_w & 3) == 0;
+    for (int t = 0; t < ntiles; ++t) {
+        if (!s_flag[t]) continue;   // (uniform)
+        const int ty = t / tm.ntx, tx = t - ty * tm.ntx;
+        const int x0 = tx * tm.tile_w, y0 = ty * tm.tile_h;
+        const int rows = min(tm.tile_h, h - y0);
+        for (int i = tid; i < rows * quads; i += 256) {
+            const int r = i / quads, x = x0 + 4 * (i - r * quads), y = y0 + r;
+            const float *pool_row = level_pool + nearest_src(y, g.sy, g.oh) * g.ow;
+            float f[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
+            if (vec_ok && x + 4 <= w) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(v + (size_t)y * w + x));
+                f[0] = q.x, f[1] = q.y, f[2] = q.z, f[3] = q.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (x + e < min(w, x0 + tm.tile_w)) f[e] = __ldg(v + (size_t)y * w + x + e);
+            }
+            int hits = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (x + e < min(w, x0 + tm.tile_w)) hits += f[e] >= __ldg(pool_row + nearest_src(x + e, g.sx, g.ow));
+            if (hits) atomicAdd(&s_rows[y], hits);
+        }
+    }
     __syncthreads();
     for (int base = 0; base < h; base += 256) {
-        const int y = base + threadIdx.x;
-        int mine = 0;
-        if (y < h) {
-            const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
-            const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
-            mine = scan_row_tiles<false>(value + ((size_t)n * h + y) * w, n, y, w, g, pool_row, tm, tile_row, nullptr, 0, 0);
-        }
+        const int y = base + tid;
+        const int mine = y < h ? s_rows[y] : 0;
         int incl = mine;
         for (int o = 1; o < 32; o <<= 1) {
             const int up = __shfl_up_sync(0xffffffffu, incl, o);
@@ -241,10 +255,10 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
         for (int k = 0; k < warp; ++k) before += s_warp[k];
         if (y < h) row_offset[(size_t)n * h + y] = before | (mine ? 0x40000000 : 0);   // bit 30: the row has hits
         __syncthreads();
-        if (threadIdx.x == 255) s_carry = before + mine;
+        if (tid == 255) s_carry = before + mine;
         __syncthreads();
     }
-    if (threadIdx.x == 0) level_total[n] = s_carry;
+    if (tid == 0) level_total[n] = s_carry;
 }
 
 __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
@@ -256,34 +270,48 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
 {
     pdl_enter();
     __shared__ long long s_sum[8];
-    __shared__ int s_any;
-    const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool last = n == levels - 1;
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
     // does this level write anything at all? (most CTAs leave here)
     int any = 0;
-    for (int y = threadIdx.x; y < h; y += 256) any |= __ldg(row_offset + (size_t)n * h + y) & 0x40000000;
-    if (any) s_any = 1;
-    __syncthreads();
-    if (!(s_any && capacity > 0) && !last) return;
+    for (int y = tid; y < h; y += 256) any |= __ldg(row_offset + (size_t)n * h + y) & 0x40000000;
+    any = __syncthreads_or(any) && capacity > 0;
+    if (!any && !last) return;
     // points of the levels before this one (the last level also publishes the grand total)
     long long sum = 0;
-    for (int k = threadIdx.x; k < n; k += 256) sum += __ldg(level_total + k);
+    for (int k = tid; k < n; k += 256) sum += __ldg(level_total + k);
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_sum[warp] = sum;
     __syncthreads();
     long long before = 0;
     for (int k = 0; k < 8; ++k) before += s_sum[k];
-    if (last && threadIdx.x == 0) *total = before + __ldg(level_total + n);
-    if (!s_any || capacity <= 0) return;
-    for (int y = threadIdx.x; y < h; y += 256) {
+    if (last && tid == 0) *total = before + __ldg(level_total + n);
+    if (!any) return;
+    const float *level_pool = pooled + (size_t)n * g.oh * g.ow;
+    const int *level_tiles = tm.data + (size_t)n * tm.nty * tm.ntx;
+    for (int y = warp; y < h; y += 8) {   // one warp per row with hits
         const int packed = __ldg(row_offset + (size_t)n * h + y);
         if (!(packed & 0x40000000)) continue;
-        const float *pool_row = pooled + ((size_t)n * g.oh + nearest_src(y, g.sy, g.oh)) * g.ow;
-        const int *tile_row = tm.data + ((size_t)n * tm.nty + y / tm.tile_h) * tm.ntx;
-        scan_row_tiles<true>(value + ((size_t)n * h + y) * w, n, y, w, g, pool_row, tm, tile_row, points,
-                             before + (packed & 0x3fffffff), capacity);
+        const float *v = value + ((size_t)n * h + y) * w;
+        const float *pool_row = level_pool + nearest_src(y, g.sy, g.oh) * g.ow;
+        long long slot = before + (packed & 0x3fffffff);
+        for (int tx = 0; tx < tm.ntx; ++tx) {
+            if (!tile_is_candidate(tm, level_tiles, y / tm.tile_h, tx, h, w, g, level_pool)) continue;
+            const int x1 = min(w, (tx + 1) * tm.tile_w);
+            for (int xb = tx * tm.tile_w; xb < x1; xb += 32) {
+                const int x = xb + lane;
+                const bool hit = x < x1 && __ldg(v + x) >= __ldg(pool_row + nearest_src(x, g.sx, g.ow));
+                const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const long long at = slot + __popc(ballot & ((1u << lane) - 1u));
+                    if (at < capacity) {
+                        reinterpret_cast<longlong2 *>(points)[at * 2] = make_longlong2(n, y);
+                        reinterpret_cast<longlong2 *>(points)[at * 2 + 1] = make_longlong2(x, 0);
+                    }
+                }
+                slot += __popc(ballot);
+            }
+        }
     }
 }
 
@@ -393,7 +421,8 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
         SILENT_LAUNCH_CHECK("window_max_kernel");
     }
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
-    if (tiles && tiles->data) {   // fused path: one CTA per level, rows skip the tiles that cannot hold a hit
+    if (tiles && tiles->data && tiles->nty * tiles->ntx <= kEmitMaxTiles && h <= kEmitMaxRows) {
+        // fused path: one CTA per level, only the tiles that can hold a hit are scanned
         SILENT_CUDA(launch_dependent(emit_count_kernel, dim3(n), dim3(256), 0, stream, value, h, w, g, (const float *)pooled,
                                      *tiles, row_offset, level_total));
         SILENT_LAUNCH_CHECK("emit_count_kernel");
