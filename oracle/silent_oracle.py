@@ -377,3 +377,28 @@ def display_tensors(orient, padded, gray, energy, centroid_region=(1, 3, 3)):
             (np.float32(255) - centroids2 * np.float32(255)).astype(np.float32),
             (fired_rgb * np.float32(255)).astype(np.float32), update_rgb, padded]                   # :98-100
     return outs, new_energy
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The reference's CPU path as it runs: scipy's own zoom (from_image.py:55-59). bench.py times this (kind
+# "reference-python"); tests check it against from_image above.
+# ----------------------------------------------------------------------------------------------------------------------
+
+def from_image_scipy(image, num_colors, center_dimensions, scale):
+    """``zoom.from_image`` with the reference's own arithmetic: per level and channel one
+    ``scipy.ndimage.zoom(crop, 1 / scale**s, order=5, prefilter=False)`` call (from_image.py:48-64), single-threaded
+    like the reference. Undefined tail rows / columns are 0 (see ``from_image``)."""
+    from scipy import ndimage
+    image = np.asarray(image, dtype=np.float32)
+    hw = image.shape[:-1]
+    h, w = list(reversed(list(center_dimensions)))
+    levels = pyramid_levels(hw, center_dimensions, scale)
+    out = np.zeros((max(levels, 0), h, w, num_colors), dtype=np.float32)
+    for s in range(levels):
+        (y0, y1), (x0, x1) = level_crop(hw, center_dimensions, scale, s)
+        crop = image[y0:y1, x0:x1]
+        for c in range(num_colors):
+            z = ndimage.zoom(crop[:, :, c], 1.0 / (scale ** s), order=5, prefilter=False)
+            ym, xm = min(h, z.shape[0]), min(w, z.shape[1])
+            out[s, :ym, :xm, c] = z[:ym, :xm]
+    return out

@@ -26,6 +26,7 @@
 // issue and shared-memory bandwidth rather than HBM.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -93,8 +94,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // ---- bulk stores (cp.async.bulk shared -> global): one instruction moves a whole staged row; the TMA unit does the
 //      address arithmetic that a per-float4 copy loop spent ~30 instructions on
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifndef SILENT_ABLATE
+#define SILENT_ABLATE 0   // experiments only: 1 no output stores, 2 no S5 arithmetic, 4 no S3 arithmetic (bit mask)
+#endif
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
 {
+    if (SILENT_ABLATE & 1) return;
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
                  : "memory");
 }
@@ -163,28 +168,35 @@ __device__ __forceinline__ void copy_out_tile(const float *__restrict__ stage, f
     }
 }
 
-// Same tile through the TMA unit: ONE bulk store per staged row (needs 16-byte aligned rows: w % 4 == 0). A warp issues
-// its lanes' bulk copies one after the other, so the 2 * TH rows are dealt to lanes 0..per_warp-1 of the warps
-// [warp0, warp0 + nwarps): with all warps of the CTA each one issues only a handful. The caller fences + barriers
-// before; every issuing thread commits its own group and must bulk_wait_read() before the staging buffer is reused.
-template <int TH, int TW>
-__device__ __forceinline__ bool copy_out_rows_bulk(const float *__restrict__ stage, float *__restrict__ out, int img0,
-                                                   int img1, bool has_b, int ty0, int tx0, int h, int w, int tid,
-                                                   int warp0, int nwarps)
+// Same tile through the TMA unit: ONE bulk store per staged row (needs 16-byte aligned rows). The `rows` staged rows
+// (2 * TH: image A's rows, then image B's) are dealt in contiguous blocks to the warps [warp0, warp0 + nwarps); lane 0 of
+// each warp issues its block in a loop whose trip count and addresses are warp-uniform (a per-lane deal made the compiler
+// serialise the lanes around the uniform-operand UBLKCP: ~20 instructions per store). row_floats: floats per global row
+// of one image (w * channels); tile_floats: floats this tile covers of a row. The caller fences + barriers before; the
+// issuing lane commits its group and must bulk_wait_read() before the staging buffer is reused.
+template <int TH>
+__device__ __forceinline__ bool bulk_rows(const float *__restrict__ stage, int stage_pitch, float *__restrict__ out,
+                                          int img0, int img1, bool has_b, int ty0, int h, size_t row_floats, size_t col0,
+                                          uint32_t tile_floats, int warp, int warp0, int nwarps, bool leader)
 {
-    constexpr int PITCH = TW * 3 + 4;
+    const int wi = warp - warp0;
+    if (wi < 0 || wi >= nwarps) return false;
     const int per_warp = (2 * TH + nwarps - 1) / nwarps;
-    const int wi = (tid >> 5) - warp0, ln = tid & 31;
-    if (wi < 0 || wi >= nwarps || ln >= per_warp) return false;
-    const int row = wi * per_warp + ln;
-    if (row < 2 * TH) {
-        const int lane = row / TH, r = row - lane * TH, gy = ty0 + r;
-        if (gy < h && (lane == 0 || has_b))
-            bulk_store(out + (((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * 3, stage + (size_t)row * PITCH,
-                       (uint32_t)(min(TW, w - tx0) * 3 * sizeof(float)));
+    const int first = wi * per_warp, last = min(first + per_warp, 2 * TH);
+    const uint32_t bytes = tile_floats * (uint32_t)sizeof(float);
+#pragma unroll
+    for (int lane = 0; lane < 2; ++lane) {   // this warp's rows of image A, then of image B: pointers step by one row
+        const int r0 = max(first, lane * TH) - lane * TH;
+        const int r1 = min(min(last, (lane + 1) * TH) - lane * TH, h - ty0);
+        if (r0 >= r1 || (lane == 1 && !has_b)) continue;
+        float *dst = out + ((size_t)(lane ? img1 : img0) * h + ty0 + r0) * row_floats + col0;
+        const float *src = stage + (size_t)(lane * TH + r0) * stage_pitch;
+#pragma unroll 1
+        for (int r = r0; r < r1; ++r, dst += row_floats, src += stage_pitch)
+            if (leader) bulk_store(dst, src, bytes);
     }
-    bulk_commit();
-    return true;
+    if (leader) bulk_commit();
+    return leader;
 }
 
 __device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[kPX])
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
         if (LOADED < T::X_PITCH) {
             for (int i = tid; i < 3 * T::X_ROWS * (T::X_PITCH - LOADED); i += NT) {
                 const int c = i % (T::X_PITCH - LOADED), rest = i / (T::X_PITCH - LOADED);
-                sX[rest * T::X_PITCH + LOADED + c] = zero2();
+                sX[(rest / T::X_ROWS) * T::X_PLANE + (rest % T::X_ROWS) * T::X_PITCH + LOADED + c] = zero2();
             }
         }
     }
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
         constexpr int TRIPLES = T::A_ROWS / 3;
         for (int t = tid; t < 3 * TRIPLES * T::A_RUNS; t += NT) {
             const int rt = t % TRIPLES, rest = t / TRIPLES;
-            const int k = rest % T::A_RUNS, c = rest / T::A_RUNS;
+            const int c = rest % 3, k = rest / 3;   // lanes walk the row triples first: conflict-free when TRIPLES % 8 == 0
             const int r0 = 3 * rt, gx0 = tx0 - 1 + kPX * k;
             f2 wt[9];
 #pragma unroll
@@ -547,25 +559,32 @@ struct ParamsB {
     WindowGeom win;   // fused region maxima (stack.h)
 };
 
-template <int TH, int TW>
+// LITE: the quick variant of stack_b. The 7x7 blur only matters where it falls below 1, and the early-out test
+// (see S4) decides that from sums over the stripe responses the tile computes anyway -- so the quick variant keeps no
+// 7x7 halo at all: the stripe stage covers the tile + 1 (what the end filter needs), the blur is never evaluated, and a
+// tile in which ANY run fails the test is left untouched and flagged for the full variant (launched right after on the
+// flagged tiles only). Less shared memory (68 KB instead of 92 KB for 24-row tiles: 3 CTAs per SM) and a third of the
+// halo arithmetic.
+template <int TH, int TW, bool LITE>
 struct TileB {
+    static constexpr int HALO_C = LITE ? 1 : 4;                   // rows of stripe output around the tile
     static constexpr int C_RUNS = (TW + 8) / kPX;                 // S3 runs start at column -4 (TW % 8 == 0)
     static constexpr int D_RUNS = (TW + 2 + kPX - 1) / kPX;       // S4 runs start at column -1
     static constexpr int E_RUNS = TW / kPX;
-    static constexpr int B_ROWS = TH + 10, CS_ROWS = TH + 8, CD_ROWS = TH + 2;
+    static constexpr int CS_ROWS = TH + 2 * HALO_C, B_ROWS = CS_ROWS + 2, CD_ROWS = TH + 2;
     static constexpr int B_PITCH = round_pitch(kPX * (C_RUNS - 1) + 10);                     // origin -5
     static constexpr int CS_PITCH = round_pitch(kPX * (D_RUNS - 1) + 14 > kPX * C_RUNS ? kPX * (D_RUNS - 1) + 14
                                                                                        : kPX * C_RUNS);   // origin -4
     static constexpr int CD_PITCH = round_pitch(kPX * D_RUNS > kPX * (E_RUNS - 1) + 10 ? kPX * D_RUNS
                                                                                        : kPX * (E_RUNS - 1) + 10);  // -1
-    static constexpr int B_PLANE = B_ROWS * B_PITCH, CS_PLANE = CS_ROWS * CS_PITCH, CD_PLANE = CD_ROWS * CD_PITCH;
+    static constexpr int B_PLANE = B_ROWS * B_PITCH, CS_PLANE = LITE ? 0 : CS_ROWS * CS_PITCH, CD_PLANE = CD_ROWS * CD_PITCH;
     // output staging (NHWC rows of one tile for both images), overlaid on sB + sCs once S4 is done. The row pitch is
     // an odd multiple of 16 B: the run-per-lane 128-bit stores AND the linear copy-out loads are conflict-free.
     static constexpr int ST_PITCH = TW * 3 + 4;                       // floats per staged row
     static constexpr int STAGE_F2 = 2 * TH * ST_PITCH / 2;            // float2 slots
     static constexpr int G_PITCH = TW + 4;                            // floats per staged gray row (odd multiple of 16 B)
     static constexpr int FRONT_F2 = B_PLANE + CS_PLANE > STAGE_F2 ? B_PLANE + CS_PLANE : STAGE_F2;
-    // maxima of the stripe channel sum over aligned groups of 4 columns ("quads", origin -4): the S4 early-out reads
+    // sums of the stripe channel sum over aligned groups of 4 columns ("quads", origin -4): the S4 early-out reads
     // 7 rows x 3 quads instead of 7 x 14 values. Two spare quads per row (never computed, always "large").
     static constexpr int Q_PITCH = round_pitch(2 * C_RUNS + 2);
     static constexpr int Q_PLANE = CS_ROWS * Q_PITCH;
@@ -578,16 +597,20 @@ struct TileB {
 // OWNOTH: an input channel of the end filter feeds the two OTHER output channels with one and the same 3x3 kernel (true
 // for rgb_2d_end_tensors): per input channel one "own" and one "other" chain, 54 FFMA2 + 6 FADD2 instead of 81 FFMA2.
 // Both orders are part of the canonical FUSED evaluation order (oracle/silent_oracle.c: so_line_end_stack_fused).
-template <int TH, int TW, int NT, bool SYM3, bool OWNOTH>
-__global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P,
-                                                     const __grid_constant__ CUtensorMap tmap, float *__restrict__ orient,
-                                                     float *__restrict__ line_end, float *__restrict__ gray,
-                                                     int *__restrict__ winmax, int *__restrict__ tilemax)
+// tile_flag [pairs][tile rows][tile cols] bytes: the LITE variant sets the flag of a tile it could not finish; the
+// full variant, given the flags, only works on flagged tiles (null: every tile).
+// One tile (bx, by) of image pair bz in a grid of nbx x nby tiles per pair.
+template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
+__device__ __forceinline__ void stack_b_tile(const int bx, const int by, const int bz, const int nbx, const int nby,
+                                             const f2 *__restrict__ bsum2, const ParamsB &P, const CUtensorMap &tmap,
+                                             float *__restrict__ orient, float *__restrict__ line_end,
+                                             float *__restrict__ gray, int *__restrict__ winmax, int *__restrict__ tilemax,
+                                             unsigned char *__restrict__ tile_flag)
 {
-    using T = TileB<TH, TW>;
+    using T = TileB<TH, TW, LITE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t tma_bar;
-    pdl_enter();
+    const size_t tile_id = ((size_t)bz * nby + by) * nbx + bx;
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
     f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
@@ -597,8 +620,10 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     float *sGray = reinterpret_cast<float *>(sCD);                // [2][TH][G_PITCH] gray staging, valid after the S5 barrier
 
     const int tid = threadIdx.x;
-    const int pair = blockIdx.z;
-    const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp index the compiler can see is warp-uniform
+    const bool leader = (tid & 31) == 0;
+    const int pair = bz;
+    const int ty0 = by * TH, tx0 = bx * TW;
     int h = P.h, w = P.w, border = P.border;
     float clip_max = P.clip_max;
     // pin the epilogue's parameters in registers now: re-reading them from the constant bank after the long S5 loop
@@ -614,7 +639,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     if (P.use_tma) {
         if (tid == 0) {   // the copy is requested before the barrier that publishes the mbarrier to the other threads
             mbar_init(&tma_bar, 1);
-            tma_load_box3(sB, &tmap, 2 * (tx0 - 4), ty0 - 5, pair, &tma_bar, (uint32_t)(T::B_PLANE * sizeof(f2)));
+            tma_load_box3(sB, &tmap, 2 * (tx0 - 4), ty0 - T::HALO_C - 1, pair, &tma_bar, (uint32_t)(T::B_PLANE * sizeof(f2)));
         }
         __syncthreads();
         mbar_wait(&tma_bar, 0);
@@ -624,7 +649,7 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
         const bool vec_ok = (w % 2) == 0;
         for (int i = tid; i < T::B_ROWS * QUADS; i += NT) {
             const int q = i % QUADS, r = i / QUADS;
-            const int gy = ty0 - 5 + r;
+            const int gy = ty0 - T::HALO_C - 1 + r;
             float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             const int x0 = tx0 - 5 + 2 * q, x1 = x0 + 1;   // plane column 2q <-> level column tx0 - 5 + 2q
             if (gy >= 0 && gy < h) {
@@ -646,15 +671,20 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
         }
     }
     __syncthreads();
+    if (!LITE && P.use_tma && tid == 0)   // every thread has seen the phase flip: a later tile of this CTA starts afresh
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&tma_bar)) : "memory");
 
     // ---- S3: c = relu(conv3x3(b, stripe)) on the channel sum; rows -4..TH+3, runs from column -4   orientation.py:24-29
     for (int t = tid; t < T::CS_ROWS * T::C_RUNS; t += NT) {
         const int r = t % T::CS_ROWS, k = t / T::CS_ROWS;
-        const int gy = ty0 - 4 + r, gx0 = tx0 - 4 + kPX * k;
+        const int gy = ty0 - T::HALO_C + r, gx0 = tx0 - 4 + kPX * k;
         f2 acc[kPX][3];
 #pragma unroll
         for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = zero2();
-        if (gy >= 0 && gy < h) {
+        if ((SILENT_ABLATE & 4) && gy >= 0 && gy < h) {
+#pragma unroll
+            for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = sB[(r + 1) * T::B_PITCH + kPX * k + p + 1];
+        } else if (gy >= 0 && gy < h) {
             if constexpr (SYM3) {
                 // chain over (b[-1,-1] + b[1,1]), (b[-1,0] + b[1,0]), (b[-1,1] + b[1,-1]), (b[0,-1] + b[0,1]), b[0,0]
                 {
@@ -715,21 +745,19 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
                 cs[p] = add2(add2(acc[p][0], acc[p][1]), acc[p][2]);
             }
         }
-        store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
-        {   // quad maxima for the S4 early-out; a quad that lies wholly outside the level can only serve pixels outside
+        if constexpr (!LITE) store_cols8(sCs + r * T::CS_PITCH + kPX * k, cs);
+        {   // quad sums for the S4 early-out; a quad that lies wholly outside the level can only serve pixels outside
             // the level (whose d is 0 whatever m is): it reads "large" so that it never forces the slow path
-            const float big = 3.0e38f;
-            f2 q0 = make_float2(fmaxf(fmaxf(cs[0].x, cs[1].x), fmaxf(cs[2].x, cs[3].x)),
-                                fmaxf(fmaxf(cs[0].y, cs[1].y), fmaxf(cs[2].y, cs[3].y)));
-            f2 q1 = make_float2(fmaxf(fmaxf(cs[4].x, cs[5].x), fmaxf(cs[6].x, cs[7].x)),
-                                fmaxf(fmaxf(cs[4].y, cs[5].y), fmaxf(cs[6].y, cs[7].y)));
+            const float big = 1.0e30f;
+            f2 q0 = add2(add2(cs[0], cs[1]), add2(cs[2], cs[3]));
+            f2 q1 = add2(add2(cs[4], cs[5]), add2(cs[6], cs[7]));
             if (gx0 + 3 < 0 || gx0 >= w) q0 = make_float2(big, big);
             if (gx0 + 7 < 0 || gx0 + 4 >= w) q1 = make_float2(big, big);
             float4 *qd = reinterpret_cast<float4 *>(sQ + r * T::Q_PITCH + 2 * k);
             qd[0] = make_float4(q0.x, q0.y, q1.x, q1.y);
             if (k == T::C_RUNS - 1) qd[1] = make_float4(big, big, big, big);   // the two spare quads of this row
         }
-        const int rd = r - 3;   // row in the CD planes (origin -1)
+        const int rd = r - (T::HALO_C - 1);   // row in the CD planes (origin -1)
         if (rd >= 0 && rd < T::CD_ROWS) {
             // column -4 + 8k + p sits at idx = 8k - 3 + p of the CD planes (origin -1): odd p starts an aligned pair
             const int base = kPX * k - 3;
@@ -749,6 +777,13 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     __syncthreads();
 
     // ---- S4: d = c * (value / pow(min(blur7x7(csum), 1), root)), in place          gaussian_regulator_tensor.py:34-36
+    // Early-out. Every blur weight is positive and every stripe response is >= 0 and finite here, so with u = 2^-24 the
+    // 49-step fmaf chain m satisfies m >= (1-u)^49 * sum(w c) >= (1 - 3e-6) * w_min * S for the sum S of ANY subset of
+    // the window. A pixel's aligned quad of columns lies inside its window for every window row, so S = the quad sums of
+    // the window rows at hand, summed in float (27 roundings: S >= S_float * (1 - 2e-6)). quick_thr is chosen on the host
+    // with w_min * quick_thr >= 1.0001, hence S_float >= quick_thr proves m > 1, where the gain is exactly reg_value
+    // (gaussian_regulator_tensor.py:35: min(m, 1)) -- bit-identical to evaluating the blur.
+    bool task_failed = false;
     for (int t = tid; t < T::CD_ROWS * T::D_RUNS; t += NT) {
         const int r = t % T::CD_ROWS, k = t / T::CD_ROWS;
         const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kPX * k;
@@ -760,20 +795,17 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             for (int co = 0; co < 3; ++co) store_cols8(sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k, z);
             continue;
         }
-        if (P.quick_thr > 0.0f) {
-            // Early-out. Every blur weight is positive and every stripe response is >= 0 and finite here, so the blur
-            // chain never decreases: m >= rn(w_min * c) for ANY c of the window. A pixel's aligned quad of columns lies
-            // inside its 7x7 window, so "the quad's maximum over the 7 window rows reaches quick_thr" proves m >= 1, where
-            // the gain is exactly reg_value (gaussian_regulator_tensor.py:35: min(m, 1)) -- bit-identical to the long way.
+        if (LITE || P.quick_thr > 0.0f) {
             f2 qa = zero2(), qb = zero2(), qc = zero2();
+            const int rs = r + T::HALO_C - 1;   // this row in the stripe-stage rows
 #pragma unroll
-            for (int ky = 0; ky < 7; ++ky) {
-                const f2 *qrow = sQ + (r + ky) * T::Q_PITCH + 2 * k;
+            for (int dy = -3; dy <= 3; ++dy) {
+                if (LITE && (rs + dy < 0 || rs + dy >= T::CS_ROWS)) continue;   // (the full variant has all 7 rows)
+                const f2 *qrow = sQ + (rs + dy) * T::Q_PITCH + 2 * k;
                 const float4 ab = *reinterpret_cast<const float4 *>(qrow);
-                const f2 c = qrow[2];
-                qa = make_float2(fmaxf(qa.x, ab.x), fmaxf(qa.y, ab.y));
-                qb = make_float2(fmaxf(qb.x, ab.z), fmaxf(qb.y, ab.w));
-                qc = make_float2(fmaxf(qc.x, c.x), fmaxf(qc.y, c.y));
+                qa = add2(qa, make_float2(ab.x, ab.y));
+                qb = add2(qb, make_float2(ab.z, ab.w));
+                qc = add2(qc, qrow[2]);
             }
             const float thr = P.quick_thr;
             float lo = fminf(fminf(qa.x, qa.y), fminf(qb.x, qb.y));
@@ -795,60 +827,71 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
                 continue;
             }
         }
-        f2 m[kPX];
-#pragma unroll
-        for (int p = 0; p < kPX; ++p) m[p] = zero2();
-#pragma unroll
-        for (int ky = 0; ky < 7; ++ky) {
-            f2 v[14];
-            load_cols<7>(sCs + (r + ky) * T::CS_PITCH + kPX * k, v);
-#pragma unroll
-            for (int kx = 0; kx < 7; ++kx)
-#pragma unroll
-                for (int p = 0; p < kPX; ++p) m[p] = fma2(P.wb[ky * 7 + kx], v[p + kx], m[p]);
-        }
-        bool all_unity = true;   // m >= 1 everywhere: the gain is exactly reg_value (the common case on textured input)
-#pragma unroll
-        for (int p = 0; p < kPX; ++p) {
-            if (kPX * k + p - 1 > TW) m[p] = make_float2(1.0f, 1.0f);   // over-computed columns of the last run
-            all_unity = all_unity && (m[p].x >= 1.0f) && (m[p].y >= 1.0f);
-        }
-        f2 gain[kPX];
-        if (all_unity) {
-#pragma unroll
-            for (int p = 0; p < kPX; ++p) gain[p] = make_float2(P.reg_value, P.reg_value);
+        if constexpr (LITE) {
+            task_failed = true;   // this tile needs the blur itself: left to the full variant
         } else {
+            f2 m[kPX];
 #pragma unroll
-            for (int p = 0; p < kPX; ++p)   // rare path (flat / dark regions): calls one out-of-line copy of the pow code
-                gain[p] = make_float2(slow_gain(m[p].x, P.reg_value, P.reg_root), slow_gain(m[p].y, P.reg_value, P.reg_root));
-        }
+            for (int p = 0; p < kPX; ++p) m[p] = zero2();
 #pragma unroll
-        for (int co = 0; co < 3; ++co) {
-            f2 *cd = sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k;
-            f2 c[kPX];
-            {
-                const float4 *p4 = reinterpret_cast<const float4 *>(cd);
+            for (int ky = 0; ky < 7; ++ky) {
+                f2 v[14];
+                load_cols<7>(sCs + (r + ky) * T::CS_PITCH + kPX * k, v);
 #pragma unroll
-                for (int q = 0; q < kPX / 2; ++q) {
-                    const float4 tq = p4[q];
-                    c[2 * q] = make_float2(tq.x, tq.y);
-                    c[2 * q + 1] = make_float2(tq.z, tq.w);
-                }
+                for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p) m[p] = fma2(P.wb[ky * 7 + kx], v[p + kx], m[p]);
             }
-            if (gx0 >= 0 && gx0 + kPX <= w) {   // (rows outside the level never get here)
+            bool all_unity = true;   // m >= 1 everywhere: the gain is exactly reg_value
 #pragma unroll
-                for (int p = 0; p < kPX; ++p) c[p] = mul2(c[p], gain[p]);
+            for (int p = 0; p < kPX; ++p) {
+                if (kPX * k + p - 1 > TW) m[p] = make_float2(1.0f, 1.0f);   // over-computed columns of the last run
+                all_unity = all_unity && (m[p].x >= 1.0f) && (m[p].y >= 1.0f);
+            }
+            f2 gain[kPX];
+            if (all_unity) {
+#pragma unroll
+                for (int p = 0; p < kPX; ++p) gain[p] = make_float2(P.reg_value, P.reg_value);
             } else {
 #pragma unroll
-                for (int p = 0; p < kPX; ++p) {
-                    const int gx = gx0 + p;
-                    c[p] = (gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
-                }
+                for (int p = 0; p < kPX; ++p)   // rare path (flat / dark regions): one out-of-line copy of the pow code
+                    gain[p] = make_float2(slow_gain(m[p].x, P.reg_value, P.reg_root), slow_gain(m[p].y, P.reg_value, P.reg_root));
             }
-            store_cols8(cd, c);
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                f2 *cd = sCD + co * T::CD_PLANE + r * T::CD_PITCH + kPX * k;
+                f2 c[kPX];
+                {
+                    const float4 *p4 = reinterpret_cast<const float4 *>(cd);
+#pragma unroll
+                    for (int q = 0; q < kPX / 2; ++q) {
+                        const float4 tq = p4[q];
+                        c[2 * q] = make_float2(tq.x, tq.y);
+                        c[2 * q + 1] = make_float2(tq.z, tq.w);
+                    }
+                }
+                if (gx0 >= 0 && gx0 + kPX <= w) {   // (rows outside the level never get here)
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p) c[p] = mul2(c[p], gain[p]);
+                } else {
+#pragma unroll
+                    for (int p = 0; p < kPX; ++p) {
+                        const int gx = gx0 + p;
+                        c[p] = (gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();   // SAME padding of the end conv
+                    }
+                }
+                store_cols8(cd, c);
+            }
         }
     }
-    __syncthreads();
+    if constexpr (LITE) {
+        if (__syncthreads_or(task_failed)) {   // nothing of this tile has been written yet
+            if (tid == 0) tile_flag[tile_id] = 1;
+            return;
+        }
+    } else {
+        __syncthreads();
+    }
 
     // ---- orient = d: restage the centre rows of the CD planes in NHWC order (same run-per-lane mapping as S5) and hand
     //      the rows to the TMA unit. When the CTA has at least two warps WITHOUT an S5 task (S5 has the fewest tasks of
@@ -880,8 +923,9 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
             __syncthreads();
         }
         if (bulk_ok) {
-            issued_orient = copy_out_rows_bulk<TH, TW>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid,
-                                                       kRestageFirst / 32, kRestageThreads / 32);
+            issued_orient = bulk_rows<TH>(sStage, T::ST_PITCH, orient, img0, img1, has_b, ty0, h, (size_t)w * 3, (size_t)tx0 * 3,
+                                          (uint32_t)(min(TW, w - tx0) * 3), warp_u, kRestageFirst / 32, kRestageThreads / 32,
+                                          leader);
         } else {
             copy_out_tile<TH, TW, kRestageThreads>(sStage, orient, img0, img1, has_b, ty0, tx0, h, w, tid - kRestageFirst);
         }
@@ -893,7 +937,10 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     const int gy = ty0 + r5, gx0 = tx0 + kPX * k5;
     const bool active = tid < TH * T::E_RUNS && gy < h && gx0 < w;
     f2 acc[kPX][3];
-    if (active) {
+    if ((SILENT_ABLATE & 2) && active) {
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) acc[p][0] = acc[p][1] = acc[p][2] = sCD[(r5 + p) * T::CD_PITCH + kPX * k5];
+    } else if (active) {
         if constexpr (OWNOTH) {
             // per input channel: own = its kernel into its own output channel, oth = the ONE kernel it feeds both other
             // output channels with; e_co = (t_0 + t_1) + t_2 with t_ci = (ci == co ? own_ci : oth_ci)
@@ -1035,23 +1082,13 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     // ---- copy-out: staged rows -> global NHWC, one bulk store per row ---------------------------------------------------
     fence_async_smem();
     __syncthreads();
-    if (gray && bulk_ok) {   // 2 * TH rows of TW floats, dealt like the line_end rows
-        const int per_warp = (2 * TH + NT / 32 - 1) / (NT / 32);
-        const int row = (tid >> 5) * per_warp + (tid & 31);
-        if ((tid & 31) < per_warp) {
-            if (row < 2 * TH) {
-                const int lane = row / TH, r = row - lane * TH, gyy = ty0 + r;
-                if (gyy < h && (lane == 0 || has_b))
-                    bulk_store(gray + ((size_t)(lane ? img1 : img0) * h + gyy) * w + tx0, sGray + (size_t)row * T::G_PITCH,
-                               (uint32_t)(min(TW, w - tx0) * sizeof(float)));
-            }
-            bulk_commit();
-            issued_line_end = true;
-        }
-    }
+    if (gray && bulk_ok)   // 2 * TH rows of TW floats, dealt like the line_end rows
+        issued_line_end |= bulk_rows<TH>(sGray, T::G_PITCH, gray, img0, img1, has_b, ty0, h, (size_t)w, (size_t)tx0,
+                                         (uint32_t)min(TW, w - tx0), warp_u, 0, NT / 32, leader);
     if (line_end) {
         if (bulk_ok) {
-            issued_line_end |= copy_out_rows_bulk<TH, TW>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid, 0, NT / 32);
+            issued_line_end |= bulk_rows<TH>(sStage, T::ST_PITCH, line_end, img0, img1, has_b, ty0, h, (size_t)w * 3,
+                                             (size_t)tx0 * 3, (uint32_t)(min(TW, w - tx0) * 3), warp_u, 0, NT / 32, leader);
         } else {
             copy_out_tile<TH, TW, NT>(sStage, line_end, img0, img1, has_b, ty0, tx0, h, w, tid);
         }
@@ -1066,9 +1103,37 @@ __global__ void __launch_bounds__(NT, 2) stack_b_kernel(const f2 *__restrict__ b
     if (tilemax && tid >= 32 && tid < 34) {   // [image][tile row][tile column], ordered-int encoding like winmax
         const int lane = tid - 32;
         if (lane == 0 || has_b)
-            tilemax[((size_t)(lane ? img1 : img0) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = sWin[8 + lane];
+            tilemax[((size_t)(lane ? img1 : img0) * nby + by) * nbx + bx] = sWin[8 + lane];
     }
     if (issued_line_end) bulk_wait_read();   // the CTA's shared memory must outlive the reads
+}
+
+// tile_flag [pairs][tile rows][tile cols] bytes. The LITE variant (one CTA per tile) sets the flag of a tile it could not
+// finish. The full variant without flags works on every tile (one CTA per tile); WITH flags it is the fix-up pass: a
+// small 1-D grid of CTAs walks the tile list and redoes the flagged tiles (none on textured input: the pass then costs
+// a few microseconds instead of a full grid of early exits).
+template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
+__global__ void __launch_bounds__(NT, LITE ? 3 : 2)
+stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, const __grid_constant__ CUtensorMap tmap,
+               float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
+               int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs)
+{
+    pdl_enter();
+    if (!LITE && tile_flag) {
+        const int per_pair = nbx * nby, total = per_pair * pairs;
+        bool again = false;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            if (!tile_flag[t]) continue;   // (uniform over the CTA)
+            if (again) __syncthreads();   // every thread is done with the previous tile's shared memory
+            again = true;
+            const int bz = t / per_pair, rest = t - bz * per_pair;
+            stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, orient, line_end,
+                                                         gray, winmax, tilemax, tile_flag);
+        }
+    } else {
+        stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, bsum2, P, tmap,
+                                                     orient, line_end, gray, winmax, tilemax, tile_flag);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1162,10 +1227,10 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
     }
     // S4 early-out threshold: the smallest float T with rn(w_min * T) >= 1 (only when every blur weight is positive)
     S->b.quick_thr = 0.0f;
-    if (blur_min > 0.0f && blur_min < INFINITY) {
-        float T = 1.0f / blur_min;
-        for (int guard = 0; guard < 8 && !(blur_min * T >= 1.0f); ++guard) T = std::nextafterf(T, INFINITY);
-        if (blur_min * T >= 1.0f && T < 1.0e30f) S->b.quick_thr = T;
+    if (blur_min > 0.0f && blur_min < INFINITY) {   // w_min * T >= 1.0001 in exact arithmetic (see S4 in stack_b_kernel)
+        float T = (float)(1.0001 / (double)blur_min);
+        for (int guard = 0; guard < 8 && !((double)blur_min * (double)T >= 1.0001); ++guard) T = std::nextafterf(T, INFINITY);
+        if ((double)blur_min * (double)T >= 1.0001 && T < 1.0e20f) S->b.quick_thr = T;
     }
     // stripe kernels symmetric under a 180-degree rotation: w3[0..4] already are the five distinct taps
     S->s3_sym = true;
@@ -1198,7 +1263,14 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
     return SILENT_OK;
 }
 
-constexpr int kTileHA = 16, kTileHB = 32;
+#ifndef SILENT_TILE_HB
+#define SILENT_TILE_HB 24
+#endif
+#ifndef SILENT_TILE_HA
+#define SILENT_TILE_HA 16
+#endif
+// stack_a tile rows: TH + 2 must be a multiple of 3 (S1 row triples); with 22 the 8 triples of a tile fill a quarter-warp
+constexpr int kTileHA = SILENT_TILE_HA, kTileHB = SILENT_TILE_HB;   // stack_b tile rows (quick and full variant share the tile grid)
 
 // Tile width: the candidate that wastes the fewest columns of the last tile (288-wide levels: 6 x 48 instead of 4.5 x 64).
 static int pick_tile_w(int w) { return ceil_div(w, 48) * 48 < ceil_div(w, 64) * 64 ? 48 : 64; }
@@ -1208,9 +1280,9 @@ struct ThreadsA {
     static constexpr int value = (TileA<kTileHA, TW>::A_ROWS * TileA<kTileHA, TW>::A_RUNS + 31) / 32 * 32;
 };
 // threads of stack_b: one warp-rounded round of its widest phase (S3), which also covers one S5 task per thread
-template <int TH, int TW>
+template <int TH, int TW, bool LITE>
 struct ThreadsB {
-    static constexpr int value = ((TH + 8) * TileB<TH, TW>::C_RUNS + 31) / 32 * 32;
+    static constexpr int value = (TileB<TH, TW, LITE>::CS_ROWS * TileB<TH, TW, LITE>::C_RUNS + 31) / 32 * 32;
 };
 
 template <int TW, bool DW, int RGBY, bool PAIRED>
@@ -1227,7 +1299,13 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
 }
 
 // room for one float2 plane per image pair (n images pair up into at most (n + levels) / 2 pairs for any pairing)
-size_t stack_workspace_bytes(int n, int h, int w) { return (size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 256; }
+// ... plus one flag byte per (pair, stack_b tile)
+static size_t stack_flag_bytes(int n, int h, int w)
+{
+    return ((size_t)(n / 2 + 8) * ceil_div(h, kTileHB) * ceil_div(w, 48) + 255) / 256 * 256;
+}
+static size_t stack_plane_bytes(int n, int h, int w) { return ((size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 255) / 256 * 256; }
+size_t stack_workspace_bytes(int n, int h, int w) { return stack_plane_bytes(n, h, w) + stack_flag_bytes(n, h, w) + 256; }
 
 // three variants: the reference's filters (depthwise rgc + shared-surround rgby), their zero patterns only, dense
 template <int TW, bool PAIRED>
@@ -1239,21 +1317,27 @@ static int dispatch_a(bool dw, bool rgby, bool shared, const void *in, const Par
     return launch_a<TW, false, 0, PAIRED>(in, P, tmap, bsum2, pairs, stream);
 }
 
-template <int TH, int TW, bool STRUCTURED>
+template <int TH, int TW, bool STRUCTURED, bool LITE>
 static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float *line_end, float *gray, int *winmax,
-                    int *tilemax, cudaStream_t stream)
+                    int *tilemax, unsigned char *tile_flag, cudaStream_t stream)
 {
     const int h = S.b.h, w = S.b.w;
     CUtensorMap map_b;
     std::memset(&map_b, 0, sizeof(map_b));
-    using TB = TileB<TH, TW>;
-    constexpr int NT = ThreadsB<TH, TW>::value;
-    auto kern = stack_b_kernel<TH, TW, NT, STRUCTURED, STRUCTURED>;
+    using TB = TileB<TH, TW, LITE>;
+    constexpr int NT = ThreadsB<TH, TW, LITE>::value;
+    auto kern = stack_b_kernel<TH, TW, NT, STRUCTURED, STRUCTURED, LITE>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
     S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
-    const dim3 grid(ceil_div(w, TW), ceil_div(h, TH), pairs);
+    const int nbx = ceil_div(w, TW), nby = ceil_div(h, TH);
+    dim3 grid(nbx, nby, pairs);
+    if (!LITE && tile_flag) {   // fix-up pass: two CTAs per SM walk the flagged tiles
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        grid = dim3((unsigned)std::min<long long>((long long)nbx * nby * pairs, 2LL * sms));
+    }
     SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, orient, line_end, gray,
-                                 winmax, tilemax));
+                                 winmax, tilemax, tile_flag, nbx, nby, pairs));
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
@@ -1273,15 +1357,22 @@ static int launch_stack_a(const void *pyr, StackPlanHost &S, bool paired_in, int
 
 template <int TW>
 static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int pairs, f2 *bsum2, float *orient,
-                        float *line_end, float *gray, int *winmax, int *tilemax, cudaStream_t stream,
-                        cudaEvent_t between_kernels)
+                        float *line_end, float *gray, int *winmax, int *tilemax, unsigned char *tile_flag,
+                        cudaStream_t stream, cudaEvent_t between_kernels)
 {
     int rc = launch_stack_a<TW>(pyr, S, paired_in, pairs, bsum2, stream);   // (96-wide stack_a tiles: measured 8 % slower)
     if (rc != SILENT_OK) return rc;
     if (between_kernels) SILENT_CUDA(cudaEventRecord(between_kernels, stream));   // stage timing hook
-    if (S.s3_sym && S.s5_ownoth)
-        return launch_b<kTileHB, TW, true>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream);
-    return launch_b<kTileHB, TW, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream);
+    if (!(S.s3_sym && S.s5_ownoth))
+        return launch_b<kTileHB, TW, false, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
+    if (!(S.b.quick_thr > 0.0f && tile_flag))
+        return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
+    // quick variant on every tile, then the full variant on the tiles it flagged (none on textured input)
+    const size_t flags = (size_t)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
+    SILENT_CUDA(cudaMemsetAsync(tile_flag, 0, flags, stream));
+    rc = launch_b<kTileHB, TW, true, true>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
+    if (rc != SILENT_OK) return rc;
+    return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
 }
 
 // Tile grid of stack_b for a level shape (the emit stage reads the per-tile maxima it writes).
@@ -1318,10 +1409,11 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     if (geo && winmax) S.b.win = *geo;
     S.a.pair_levels = S.b.pair_levels = levels;
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    unsigned char *tile_flag = reinterpret_cast<unsigned char *>(bsum2) + stack_plane_bytes(n, h, w);
     if (pick_tile_w(w) == 48)
-        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream,
+        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream,
                                 between_kernels);
-    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, stream,
+    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream,
                             between_kernels);
 }
 

@@ -247,3 +247,13 @@ def test_shim_resize_nearest_matches_torch(h, w, oh, ow):
     got = T.resize_images(x, [oh, ow], method=T._ResizeMethod.NEAREST_NEIGHBOR).numpy()
     want = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), size=(oh, ow), mode="nearest")
     assert np.array_equal(got, want.permute(0, 2, 3, 1).numpy())
+
+
+def test_scipy_pyramid_is_the_literal_pyramid():
+    """bench.py's "reference-python" CPU arm calls scipy.ndimage.zoom exactly like from_image.py:55-59; the literal
+    oracle's own spline code reproduces it to float32 rounding."""
+    pytest.importorskip("scipy")
+    frame = synthetic_frame(1, 0, 240, 320)
+    a = lit.from_image_scipy(frame, 3, (96, 64), 1.5)
+    b = lit.from_image(frame, 3, (96, 64), 1.5)
+    assert a.shape == b.shape and np.abs(a - b).max() <= 1e-5 * 255
