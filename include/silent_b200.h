@@ -68,6 +68,20 @@ typedef struct silent_stack_weights {
     int32_t border;              /* 2,     recognition_testing.py:75 */
 } silent_stack_weights;
 
+/* Orientation BANK of BASELINE config C4: 8 orientations built with the reference's per-vector generators
+ * stripe_tensor (edge_orientation_detector/stripe_tensor.py:21-70, [3,3,8,8] sliced to its first 3 input channels),
+ * blur_tensor(2, 7, 8, 8) (gaussian_blur/gaussian_blur.py:13-54) and end_tensor (oriented_end_detector.py:13-55). */
+#define SILENT_BANK 8
+typedef struct silent_bank_weights {
+    float rgc[3 * 3 * 3 * 3];
+    float rgby[3 * 3 * 3 * 3];
+    float stripe[3 * 3 * 3 * SILENT_BANK];          /* identical over the 3 input channels */
+    float blur[7 * 7 * SILENT_BANK * SILENT_BANK];  /* every slice identical */
+    float end[3 * 3 * SILENT_BANK * SILENT_BANK];   /* depthwise: orientation k only feeds orientation k */
+    float regulation_value, regulation_root, clip_max;
+    int32_t border;
+} silent_bank_weights;
+
 int silent_abi_version(void);
 const char *silent_last_error(void);
 /* Number of CUDA kernels this library has launched in this process so far (bench.py reports the delta per step). */
@@ -206,6 +220,13 @@ int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const sile
 int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_host, const void *frames_dev, int batch,
                         float *pyramid_dev, float *orient_dev, float *line_end_dev, int64_t *points_dev,
                         int64_t capacity, int64_t *count_dev, silent_stream stream);
+
+/* The same path with the 8-orientation bank (config C4): frames -> pyramid -> rgc -> rgby -> stripe bank -> regulator ->
+ * end bank -> mask -> mean -> feature points; orient_dev / line_end_dev are [batch*L, h, w, 8]. uint8 frames with 3 colours
+ * only; SILENT_E_STRUCTURE when the bank lacks the generators' structure (use the per-operator calls then). */
+int silent_pipeline_run_bank(silent_plan *plan, const silent_bank_weights *weights_host, const void *frames_dev, int batch,
+                             float *orient_dev, float *line_end_dev, int64_t *points_dev, int64_t capacity,
+                             int64_t *count_dev, silent_stream stream);
 
 /* Measurement hook: when enabled, silent_pipeline_run brackets its stages with CUDA events on the launching stream.
  * silent_plan_stage_ms synchronises those events and returns the device time of the LAST run's pyramid, fused-stack and

@@ -74,6 +74,8 @@ def lib():
         for name in ("so_depthwise3", "so_rgby_shared", "so_stripe_sym180", "so_end_ownoth"):
             getattr(L, name).restype = c_int
             getattr(L, name).argtypes = [_f32p]
+        L.so_rgc_rgby_fused.restype = None
+        L.so_rgc_rgby_fused.argtypes = [_f32p, c_int, c_int, c_int, _f32p, _f32p, _f32p, _f32p]
         L.so_get_centroids.restype = None
         L.so_get_centroids.argtypes = [_f32p, c_int, c_int, c_int, c_int, c_int, _f32p, _f32p, _f32p]
         L.so_resize_nearest.restype = None
@@ -211,6 +213,26 @@ def line_end_stack(pyramid, weights, region_divisor=2.0, order="fused"):
         pts = np.zeros((0, 4), np.int64)
     bufs.update(gray=gray, points=pts)
     return bufs
+
+
+def bank_stack(pyramid, f, region_hw, order="fused"):
+    """BASELINE config C4: S1-S2 on 3 channels, S3-S7 on the orientation bank ``f`` (dict rgc, rgby, stripe [3,3,3,C],
+    blur [7,7,C,C], end [3,3,C,C]), composed like ``compile()`` (recognition_testing.py:69-77). ``order="fused"``: rgc /
+    rgby as the fused kernels evaluate them (shared-surround order); every other stage is the per-operator chain (the
+    bank kernel skips exact-zero weights only, which does not change a bit)."""
+    x = _c(pyramid)
+    n, h, w, _ = x.shape
+    if order == "fused":
+        a, b = np.empty_like(x), np.empty_like(x)
+        lib().so_rgc_rgby_fused(x, n, h, w, _c(f["rgc"]), _c(f["rgby"]), a, b)
+    else:
+        b = conv2d(conv2d(x, f["rgc"], post=1), f["rgby"], post=1)
+    orient = regulate_tensor(conv2d(b, f["stripe"], post=1), f["blur"], 1.0, .1)
+    line_end = conv2d(orient, f["end"], post=2, clip_hi=255.0)
+    padded = pad_inwards(line_end, [[0, 0], [2, 2], [2, 2], [0, 0]])
+    gray = get_value_from_color(padded)
+    points, _ = max_value_indices_region(gray, region_hw)
+    return dict(orient=orient, padded=padded, gray=gray, points=points)
 
 
 # ---- "next" rows: centroids, nearest resize, boosting, display arithmetic ------------------------------------------------

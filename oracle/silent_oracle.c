@@ -504,6 +504,15 @@ static void so_conv_end_ownoth(const float *d, int N, int h, int w, const float 
             }
 }
 
+/* S1 + S2 as the fused kernels evaluate them (stack_a_kernel): a = relu(rgc * x), b = relu(rgby * a) with the shared-
+ * surround order when both structures hold. Used by the orientation-bank composition (config C4). */
+void so_rgc_rgby_fused(const float *pyr, int N, int h, int w, const float *rgc, const float *rgby, float *a, float *b)
+{
+    so_conv2d(pyr, N, h, w, 3, rgc, 3, 3, 3, 1, 0.0f, a);
+    if (so_depthwise3(rgc) && so_rgby_shared(rgby)) so_conv_rgby_shared(a, N, h, w, rgby, b);
+    else so_conv2d(a, N, h, w, 3, rgby, 3, 3, 3, 1, 0.0f, b);
+}
+
 /* Same buffers as so_line_end_stack. Which stage takes its structured order mirrors the kernels' dispatch:
  * S2 shared needs a depthwise rgc as well (one stack_a variant), S3 symmetric and S5 own/other go together. */
 void so_line_end_stack_fused(const float *pyr, int N, int h, int w, const float *rgc, const float *rgby,

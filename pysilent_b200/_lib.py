@@ -24,7 +24,7 @@ SYMBOLS = (
     "silent_plan_level_tables", "silent_plan_algorithmic_bytes", "silent_pyramid_build", "silent_conv2d",
     "silent_regulate", "silent_pad_inwards", "silent_value_from_color", "silent_selection_workspace_bytes",
     "silent_max_value_indices_region", "silent_top_value_points", "silent_stack_workspace_bytes", "silent_stack_fused", "silent_pipeline_run",
-    "silent_pipeline_run_host", "silent_get_centroids", "silent_resize_nearest", "silent_get_boosting", "silent_pointwise", "silent_pack_points",
+    "silent_pipeline_run_host", "silent_pipeline_run_bank", "silent_get_centroids", "silent_resize_nearest", "silent_get_boosting", "silent_pointwise", "silent_pack_points",
 )
 
 
@@ -38,6 +38,14 @@ class SilentStackWeights(ctypes.Structure):
     _fields_ = [("rgc", ctypes.c_float * 81), ("rgby", ctypes.c_float * 81), ("stripe", ctypes.c_float * 81),
                 ("blur", ctypes.c_float * 441), ("end", ctypes.c_float * 81), ("regulation_value", ctypes.c_float),
                 ("regulation_root", ctypes.c_float), ("clip_max", ctypes.c_float), ("border", ctypes.c_int32)]
+
+
+class SilentBankWeights(ctypes.Structure):
+    """silent_bank_weights: the 8-orientation bank of BASELINE config C4."""
+    _fields_ = [("rgc", ctypes.c_float * 81), ("rgby", ctypes.c_float * 81), ("stripe", ctypes.c_float * (9 * 3 * 8)),
+                ("blur", ctypes.c_float * (49 * 64)), ("end", ctypes.c_float * (9 * 64)),
+                ("regulation_value", ctypes.c_float), ("regulation_root", ctypes.c_float), ("clip_max", ctypes.c_float),
+                ("border", ctypes.c_int32)]
 
 
 _lib = None
@@ -83,6 +91,7 @@ def lib():
         "silent_stack_fused": (i, [p, i, i, i, ctypes.POINTER(SilentStackWeights), p, p, p, p, sz, p]),
         "silent_pipeline_run": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, p, i64, p, p]),
         "silent_pipeline_run_host": (i, [p, ctypes.POINTER(SilentStackWeights), p, i, p, p, p, i64, p, p]),
+        "silent_pipeline_run_bank": (i, [p, ctypes.POINTER(SilentBankWeights), p, i, p, p, p, i64, p, p]),
         "silent_get_centroids": (i, [p, i, i, i, i, i, p, p, p, p]),
         "silent_resize_nearest": (i, [p, i, i, i, i, i, i, p, p]),
         "silent_get_boosting": (i, [p, p, i, i, i, f, f, i, p, p, p]),
@@ -114,6 +123,19 @@ def make_stack_weights(rgc, rgby, stripe, blur, end, regulation_value=1.0, regul
         a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
         if a.shape != shape:
             raise ValueError("fused stack needs %s of shape %s, got %s" % (name, shape, a.shape))
+        ctypes.memmove(getattr(w, name), a.ctypes.data, a.nbytes)
+    w.regulation_value, w.regulation_root, w.clip_max, w.border = regulation_value, regulation_root, clip_max, border
+    return w
+
+
+def make_bank_weights(rgc, rgby, stripe, blur, end, regulation_value=1.0, regulation_root=.1, clip_max=255.0, border=2):
+    """Pack the 8-orientation bank (HWIO, any float dtype) into ``silent_bank_weights``."""
+    w = SilentBankWeights()
+    for name, arr, shape in (("rgc", rgc, (3, 3, 3, 3)), ("rgby", rgby, (3, 3, 3, 3)), ("stripe", stripe, (3, 3, 3, 8)),
+                             ("blur", blur, (7, 7, 8, 8)), ("end", end, (3, 3, 8, 8))):
+        a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
+        if a.shape != shape:
+            raise ValueError("the fused orientation bank needs %s of shape %s, got %s" % (name, shape, a.shape))
         ctypes.memmove(getattr(w, name), a.ctypes.data, a.nbytes)
     w.regulation_value, w.regulation_root, w.clip_max, w.border = regulation_value, regulation_root, clip_max, border
     return w

@@ -4,10 +4,18 @@
 #include <algorithm>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "plan.h"
 #include "stack.h"
 
 namespace silent {
+
+// NVTX range over a stage's launches (free when no profiler is attached; shows the stage next to its kernels in nsys)
+struct StageRange {
+    explicit StageRange(const char *name) { nvtxRangePushA(name); }
+    ~StageRange() { nvtxRangePop(); }
+};
 
 static void release(Workspace &ws)
 {
@@ -139,15 +147,19 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
     int rc = SILENT_OK;
     // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
     // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
-    if (pyramid_dev || !pair_path) {
-        float *dst = pyramid_dev ? pyramid_dev + img0 * level_elems * plan->params.num_colors : ws.d_pyramid;
-        rc = pyramid_build(plan, frames, nb, dst, s);
-        if (rc != SILENT_OK) return rc;
+    {
+        StageRange range("silent:pyramid");
+        if (pyramid_dev || !pair_path) {
+            float *dst = pyramid_dev ? pyramid_dev + img0 * level_elems * plan->params.num_colors : ws.d_pyramid;
+            rc = pyramid_build(plan, frames, nb, dst, s);
+            if (rc != SILENT_OK) return rc;
+        }
+        if (pair_path) {
+            rc = pyramid_pair_build(plan, frames, nb, ws.d_pyramid, s);
+            if (rc != SILENT_OK) return rc;
+        }
     }
-    if (pair_path) {
-        rc = pyramid_pair_build(plan, frames, nb, ws.d_pyramid, s);
-        if (rc != SILENT_OK) return rc;
-    }
+    StageRange range("silent:stack");
     const void *pyr = pair_path ? (const void *)ws.d_pyramid
                                 : (const void *)(pyramid_dev ? pyramid_dev + img0 * level_elems * 3 : ws.d_pyramid);
     if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
@@ -192,11 +204,47 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
     if (rc != SILENT_OK) return rc;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
     if (count_dev) {
+        StageRange range("silent:emit");
         const TileMaxima tm = tile_maxima(plan);
         rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
                                       count_dev, ws.d_select, ws.select_bytes, fuse_windows ? ws.d_winmax : nullptr, &tm, s);
     }
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[3], s));
+    return rc;
+}
+
+int silent_pipeline_run_bank(silent_plan *plan, const silent_bank_weights *weights_host, const void *frames_dev, int batch,
+                             float *orient_dev, float *line_end_dev, int64_t *points_dev, int64_t capacity,
+                             int64_t *count_dev, silent_stream stream)
+{
+    if (!plan || !weights_host || !frames_dev) return fail(SILENT_E_INVAL, "silent_pipeline_run_bank: null argument");
+    if (batch <= 0) return fail(SILENT_E_INVAL, "batch must be positive");
+    if (plan->levels == 0) return fail(SILENT_E_SHAPE, "frame is not larger than the pyramid centre: 0 levels");
+    if (!pyramid_pair_supported(plan))
+        return fail(SILENT_E_SHAPE, "silent_pipeline_run_bank needs uint8 frames with 3 colours (frame-pair pyramid path)");
+    if ((plan->h % 2) || (plan->w % 2))
+        return fail(SILENT_E_SHAPE, "Ambiguous dimension: region shape (h/2, w/2) must be integral (h=%d, w=%d)", plan->h,
+                    plan->w);
+    Workspace &ws = plan->ws;
+    if (ws.batch < batch)
+        return fail(SILENT_E_CAPACITY, "plan workspace holds %d frames, need %d: call silent_plan_reserve", ws.batch, batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = batch * plan->levels;
+    if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[0], s));
+    int rc = pyramid_pair_build(plan, frames_dev, batch, ws.d_pyramid, s);
+    if (rc != SILENT_OK) return rc;
+    if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[1], s));
+    rc = stack_bank(ws.d_pyramid, n, plan->h, plan->w, plan->levels, weights_host, orient_dev, line_end_dev, ws.d_gray,
+                    ws.d_stack, ws.stack_bytes, s);
+    if (rc != SILENT_OK) return rc;
+    if (plan->timing) {
+        SILENT_CUDA(cudaEventRecord(plan->ev_mid, s));
+        SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
+    }
+    if (count_dev)
+        rc = max_value_indices_region(ws.d_gray, n, plan->h, plan->w, plan->h / 2, plan->w / 2, points_dev, capacity,
+                                      count_dev, ws.d_select, ws.select_bytes, nullptr, nullptr, s);
+    if (plan->timing) SILENT_CUDA(cudaEventRecord(plan->ev[3], s));
     return rc;
 }
 

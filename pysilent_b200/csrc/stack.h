@@ -24,6 +24,10 @@ struct TileMaxima {
     int tile_h = 0, tile_w = 0, nty = 0, ntx = 0;
 };
 
+// orientation bank (config C4): xpair (pyramid_pair_kernel layout) -> orient / line_end [n,h,w,8], gray [n,h,w]
+int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const silent_bank_weights *W, float *orient,
+               float *line_end, float *gray, void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
 // pyramid.cu
 int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
 bool pyramid_pair_supported(const silent_plan *plan);

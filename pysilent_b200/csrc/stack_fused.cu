@@ -1137,6 +1137,291 @@ stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// kernel BANK: stack_b for an orientation BANK (BASELINE config C4: 8 orientations through the reference's per-vector
+// generators, stripe_tensor.py:21-70 / oriented_end_detector.py:13-55 / gaussian_blur.py:13-54):
+//   bsum2 -> stripe bank 1 -> NB (identical over the rgby channels, so it runs on the channel sum like S3) -> regulator
+//   (one 7x7 blur of the NB-channel sum, all NB x NB slices identical) -> end bank, DEPTHWISE (orientation k only feeds
+//   orientation k) + relu + clip -> border mask -> mean. Outputs orient / padded_line_end [n, h, w, NB], gray [n, h, w].
+// Same building blocks as stack_b_kernel (frame pairs in float2 lanes, lanes walk rows over odd-multiple-of-16-byte
+// pitches, staged NHWC rows leaving through bulk stores, the quad-sum early-out of the blur) with runs of 4 pixels, so
+// that 4 orientations x 4 pixels of results fit in registers at a time. Chains run in the canonical (ky, kx) order of
+// the per-operator kernels: skipping the end bank's exact-zero cross-orientation weights is a no-op for finite data.
+// ---------------------------------------------------------------------------------------------------------------------
+
+constexpr int kNB = 8;   // orientations of the bank
+constexpr int kRun = 4;  // pixels per run
+
+struct ParamsBank {
+    f2 w3[9][kNB];   // stripe [tap][orientation]
+    f2 wb[49];       // blur
+    f2 w5[9][kNB];   // end, depthwise [tap][orientation]
+    float reg_value, reg_root, clip_max, quick_thr;
+    int border, h, w, n, pair_levels;
+};
+
+template <int TH, int TW>
+struct TileBank {
+    static constexpr int C_RUNS = (TW + 9 + kRun - 1) / kRun;   // stripe runs start at column -5 (need -4 .. TW + 3)
+    static constexpr int D_RUNS = (TW + 2 + kRun - 1) / kRun;   // regulator runs start at column -1
+    static constexpr int E_RUNS = TW / kRun;
+    static constexpr int B_ROWS = TH + 10, CS_ROWS = TH + 8, CD_ROWS = TH + 2;   // row origins -5, -4, -1
+    static constexpr int B_PITCH = round_pitch(kRun * (C_RUNS - 1) + 6);          // column origin -6
+    static constexpr int CS_PITCH = round_pitch(kRun * (D_RUNS - 1) + 12 > kRun * C_RUNS ? kRun * (D_RUNS - 1) + 12
+                                                                                         : kRun * C_RUNS);   // origin -5
+    static constexpr int CD_PITCH = round_pitch(kRun * D_RUNS > kRun * (E_RUNS - 1) + 6 ? kRun * D_RUNS
+                                                                                       : kRun * (E_RUNS - 1) + 6);   // -1
+    static constexpr int Q_PITCH = C_RUNS | 1;                                     // one quad sum per stripe run
+    static constexpr int B_PLANE = B_ROWS * B_PITCH, CS_PLANE = CS_ROWS * CS_PITCH, CD_PLANE = CD_ROWS * CD_PITCH;
+    static constexpr int ST_PITCH = TW * kNB + 4;                    // floats per staged NHWC row (odd multiple of 16 B)
+    static constexpr int STAGE_F2 = 2 * TH * ST_PITCH / 2;
+    static constexpr int FRONT_F2 = B_PLANE + CS_PLANE > STAGE_F2 ? B_PLANE + CS_PLANE : STAGE_F2;
+    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + kNB * CD_PLANE + CS_ROWS * Q_PITCH) * sizeof(f2) + 64;
+    static_assert(TW % kRun == 0 && TW % 4 == 0, "tile width must be a multiple of the run length");
+};
+
+__device__ __forceinline__ void store_cols4(f2 *__restrict__ dst, const f2 (&v)[kRun])
+{
+    float4 *p = reinterpret_cast<float4 *>(dst);
+    p[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+    p[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+}
+
+template <int TH, int TW, int NT>
+__global__ void __launch_bounds__(NT, 2) stack_bank_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsBank P,
+                                                           float *__restrict__ orient, float *__restrict__ line_end,
+                                                           float *__restrict__ gray)
+{
+    using T = TileBank<TH, TW>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_enter();
+    f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]      rgby channel sum, origin (-5, -6)
+    f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]    sum of the stripe bank, origin (-4, -5)
+    f2 *sCD = sB + T::FRONT_F2;                  // [NB][CD_ROWS][CD_PITCH] stripe bank, regulated in place, origin (-1, -1)
+    f2 *sQ = sCD + kNB * T::CD_PLANE;            // [CS_ROWS][Q_PITCH]     quad sums of sCs
+    float *sStage = reinterpret_cast<float *>(sB);   // [2][TH][ST_PITCH] NHWC staging, valid after the S4 barrier
+
+    const int tid = threadIdx.x;
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const bool leader = (tid & 31) == 0;
+    const int pair = blockIdx.z, ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+    const int h = P.h, w = P.w;
+    int img0, img1;
+    bool has_b;
+    pair_images(pair, P.pair_levels, P.n, img0, img1, has_b);
+
+    // ---- channel-sum tile (pixel x lives in column x + 1 of the (w + 2)-wide rows), zero outside the level -----------
+    {
+        const f2 *src = bsum2 + (size_t)pair * h * (w + 2) + 1;
+        for (int i = tid; i < T::B_ROWS * T::B_PITCH; i += NT) {
+            const int c = i % T::B_PITCH, r = i / T::B_PITCH;
+            const int gy = ty0 - 5 + r, gx = tx0 - 6 + c;
+            sB[i] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? __ldg(src + (size_t)gy * (w + 2) + gx) : zero2();
+        }
+    }
+    __syncthreads();
+
+    // ---- S3: stripe bank on the channel sum; rows -4 .. TH+3, runs of 4 columns from -5 ------------------------------
+    for (int t = tid; t < T::CS_ROWS * T::C_RUNS; t += NT) {
+        const int r = t % T::CS_ROWS, k = t / T::CS_ROWS;
+        const int gy = ty0 - 4 + r, gx0 = tx0 - 5 + kRun * k;
+        const bool row_ok = gy >= 0 && gy < h;
+        f2 v[3][6];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) load_cols<3>(sB + (r + ky) * T::B_PITCH + kRun * k, v[ky]);
+        f2 cs[kRun];
+#pragma unroll
+        for (int p = 0; p < kRun; ++p) cs[p] = zero2();
+        const int rd = r - 3;   // row in the CD planes
+#pragma unroll
+        for (int o = 0; o < kNB; ++o) {
+            f2 acc[kRun];
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) acc[p] = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kRun; ++p) acc[p] = fma2(P.w3[ky * 3 + kx][o], v[ky][p + kx], acc[p]);
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) {
+                const int gx = gx0 + p;
+                acc[p] = (row_ok && gx >= 0 && gx < w) ? relu2_finite(acc[p]) : zero2();   // SAME padding downstream
+                cs[p] = o == 0 ? acc[p] : add2(cs[p], acc[p]);                             // ((c0 + c1) + c2) + ...
+            }
+            if (rd >= 0 && rd < T::CD_ROWS && k >= 1 && kRun * (k - 1) + kRun <= T::CD_PITCH)
+                store_cols4(sCD + o * T::CD_PLANE + rd * T::CD_PITCH + kRun * (k - 1), acc);
+        }
+        store_cols4(sCs + r * T::CS_PITCH + kRun * k, cs);
+        f2 q = add2(add2(cs[0], cs[1]), add2(cs[2], cs[3]));
+        if (gx0 + kRun - 1 < 0 || gx0 >= w) q = make_float2(1.0e30f, 1.0e30f);   // wholly outside: never forces the blur
+        sQ[r * T::Q_PITCH + k] = q;
+    }
+    __syncthreads();
+
+    // ---- S4: regulator, in place; rows -1 .. TH, runs of 4 from column -1 (quad of run j = stripe run j + 1) -----------
+    for (int t = tid; t < T::CD_ROWS * T::D_RUNS; t += NT) {
+        const int r = t % T::CD_ROWS, j = t / T::CD_ROWS;
+        const int gy = ty0 - 1 + r, gx0 = tx0 - 1 + kRun * j;
+        if (gy < 0 || gy >= h) continue;   // the planes already hold zeros there
+        bool unity = false;
+        if (P.quick_thr > 0.0f) {   // see stack_b_kernel S4: quad sums of the 7 window rows prove m >= 1
+            f2 qs = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) qs = add2(qs, sQ[(r + ky) * T::Q_PITCH + j + 1]);
+            unity = fminf(qs.x, qs.y) >= P.quick_thr;
+        }
+        f2 gain[kRun];
+        if (unity) {
+            if (P.reg_value == 1.0f) continue;
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) gain[p] = make_float2(P.reg_value, P.reg_value);
+        } else {
+            f2 m[kRun];
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) m[p] = zero2();
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky) {
+                f2 cv[12];   // Cs columns 4j .. 4j+11 (level columns gx0 - 4 .. gx0 + 7); pixel p uses 1 + p .. 7 + p
+                load_cols<6>(sCs + (r + ky) * T::CS_PITCH + kRun * j, cv);
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                    for (int p = 0; p < kRun; ++p) m[p] = fma2(P.wb[ky * 7 + kx], cv[1 + p + kx], m[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < kRun; ++p)
+                gain[p] = make_float2(slow_gain(m[p].x, P.reg_value, P.reg_root), slow_gain(m[p].y, P.reg_value, P.reg_root));
+        }
+#pragma unroll
+        for (int o = 0; o < kNB; ++o) {
+            f2 *cd = sCD + o * T::CD_PLANE + r * T::CD_PITCH + kRun * j;
+            f2 c[4];
+            load_cols<2>(cd, c);
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) {
+                const int gx = gx0 + p;
+                c[p] = (gx >= 0 && gx < w) ? mul2(c[p], gain[p]) : zero2();
+            }
+            store_cols4(cd, c);
+        }
+    }
+    __syncthreads();
+
+    // ---- orient = d: centre rows of the planes, restaged NHWC (4 orientations = one 128-bit chunk per pixel and image) --
+    const bool bulk_ok = (w % 4) == 0;
+    bool issued = false;
+    if (orient) {
+        for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+            const int r = t % TH, k = t / TH;
+#pragma unroll
+            for (int g = 0; g < kNB / 4; ++g) {
+                f2 d[4][6];
+#pragma unroll
+                for (int oo = 0; oo < 4; ++oo) load_cols<3>(sCD + (4 * g + oo) * T::CD_PLANE + (r + 1) * T::CD_PITCH + kRun * k, d[oo]);
+#pragma unroll
+                for (int p = 0; p < kRun; ++p) {
+                    float *a = sStage + (size_t)r * T::ST_PITCH + (kRun * k + p) * kNB + 4 * g;
+                    float *b = sStage + (size_t)(TH + r) * T::ST_PITCH + (kRun * k + p) * kNB + 4 * g;
+                    *reinterpret_cast<float4 *>(a) = make_float4(d[0][p + 1].x, d[1][p + 1].x, d[2][p + 1].x, d[3][p + 1].x);
+                    *reinterpret_cast<float4 *>(b) = make_float4(d[0][p + 1].y, d[1][p + 1].y, d[2][p + 1].y, d[3][p + 1].y);
+                }
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (bulk_ok) {
+            issued = bulk_rows<TH>(sStage, T::ST_PITCH, orient, img0, img1, has_b, ty0, h, (size_t)w * kNB, (size_t)tx0 * kNB,
+                                   (uint32_t)(min(TW, w - tx0) * kNB), warp_u, 0, NT / 32, leader);
+        } else {
+            for (int i = tid; i < 2 * TH * TW * kNB; i += NT) {
+                const int e = i % (TW * kNB), row = i / (TW * kNB), lane = row / TH, gy = ty0 + row % TH;
+                if (gy < h && tx0 + e / kNB < w && (lane == 0 || has_b))
+                    orient[(((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * kNB + e] = sStage[(size_t)row * T::ST_PITCH + e];
+            }
+        }
+        if (issued) bulk_wait_read();
+        __syncthreads();   // the staging buffer is free again
+    }
+
+    // ---- S5-S7: depthwise end bank + relu + clip, border mask, mean over the orientations --------------------------------
+    const float inv_nb = __fdiv_rn(1.0f, (float)kNB);
+    for (int t = tid; t < TH * T::E_RUNS; t += NT) {
+        const int r = t % TH, k = t / TH;
+        const int gy = ty0 + r, gx0 = tx0 + kRun * k;
+        const bool row_in = gy >= P.border && gy < h - P.border;
+        f2 g[kRun];
+#pragma unroll
+        for (int gq = 0; gq < kNB / 4; ++gq) {
+            f2 e[4][kRun];
+#pragma unroll
+            for (int oo = 0; oo < 4; ++oo) {
+                const int o = 4 * gq + oo;
+#pragma unroll
+                for (int p = 0; p < kRun; ++p) e[oo][p] = zero2();
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    f2 v[6];
+                    load_cols<3>(sCD + o * T::CD_PLANE + (r + ky) * T::CD_PITCH + kRun * k, v);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int p = 0; p < kRun; ++p) e[oo][p] = fma2(P.w5[ky * 3 + kx][o], v[p + kx], e[oo][p]);
+                }
+#pragma unroll
+                for (int p = 0; p < kRun; ++p) {
+                    f2 x = make_float2(clip_nan(relu_nan(e[oo][p].x), P.clip_max), clip_nan(relu_nan(e[oo][p].y), P.clip_max));
+                    const int gx = gx0 + p;
+                    if (!(row_in && gx >= P.border && gx < w - P.border))   // pad_inwards multiplies by 0: NaN stays NaN
+                        x = make_float2(x.x != x.x ? x.x : 0.0f * x.x, x.y != x.y ? x.y : 0.0f * x.y);
+                    e[oo][p] = x;
+                    g[p] = o == 0 ? x : add2(g[p], x);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kRun; ++p) {
+                float *a = sStage + (size_t)r * T::ST_PITCH + (kRun * k + p) * kNB + 4 * gq;
+                float *b = sStage + (size_t)(TH + r) * T::ST_PITCH + (kRun * k + p) * kNB + 4 * gq;
+                *reinterpret_cast<float4 *>(a) = make_float4(e[0][p].x, e[1][p].x, e[2][p].x, e[3][p].x);
+                *reinterpret_cast<float4 *>(b) = make_float4(e[0][p].y, e[1][p].y, e[2][p].y, e[3][p].y);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < kRun; ++p) g[p] = mul2(g[p], make_float2(inv_nb, inv_nb));
+        if (gray) {   // few bytes: written straight from registers (4 consecutive floats per image)
+            if (bulk_ok && gx0 + kRun <= w && gy < h) {
+                *reinterpret_cast<float4 *>(gray + ((size_t)img0 * h + gy) * w + gx0) = make_float4(g[0].x, g[1].x, g[2].x, g[3].x);
+                if (has_b)
+                    *reinterpret_cast<float4 *>(gray + ((size_t)img1 * h + gy) * w + gx0) = make_float4(g[0].y, g[1].y, g[2].y, g[3].y);
+            } else if (gy < h) {
+#pragma unroll
+                for (int p = 0; p < kRun; ++p)
+                    if (gx0 + p < w) {
+                        gray[((size_t)img0 * h + gy) * w + gx0 + p] = g[p].x;
+                        if (has_b) gray[((size_t)img1 * h + gy) * w + gx0 + p] = g[p].y;
+                    }
+            }
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    issued = false;
+    if (line_end) {
+        if (bulk_ok) {
+            issued = bulk_rows<TH>(sStage, T::ST_PITCH, line_end, img0, img1, has_b, ty0, h, (size_t)w * kNB, (size_t)tx0 * kNB,
+                                   (uint32_t)(min(TW, w - tx0) * kNB), warp_u, 0, NT / 32, leader);
+        } else {
+            for (int i = tid; i < 2 * TH * TW * kNB; i += NT) {
+                const int e = i % (TW * kNB), row = i / (TW * kNB), lane = row / TH, gy = ty0 + row % TH;
+                if (gy < h && tx0 + e / kNB < w && (lane == 0 || has_b))
+                    line_end[(((size_t)(lane ? img1 : img0) * h + gy) * w + tx0) * kNB + e] = sStage[(size_t)row * T::ST_PITCH + e];
+            }
+        }
+    }
+    if (issued) bulk_wait_read();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 
@@ -1417,6 +1702,79 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
                             between_kernels);
 }
 
+
+// ---- orientation bank (config C4): S1-S2 through stack_a, then stack_bank_kernel ------------------------------------------
+constexpr int kBankTH = 16, kBankTW = 32;
+
+int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const silent_bank_weights *W, float *orient,
+               float *line_end, float *gray, void *workspace, size_t workspace_bytes, cudaStream_t stream)
+{
+    if (!xpair || !W) return fail(SILENT_E_INVAL, "silent_pipeline_run_bank: null argument");
+    if (pair_levels <= 0 || n % pair_levels != 0) return fail(SILENT_E_INVAL, "bank stack: n must be whole frames");
+    const int pairs = ((n / pair_levels + 1) / 2) * pair_levels;
+    if (pairs > 65535) return fail(SILENT_E_SHAPE, "bank stack: at most 65535 image pairs per call");
+    if (!workspace || workspace_bytes < stack_workspace_bytes(n, h, w))
+        return fail(SILENT_E_CAPACITY, "bank stack: workspace too small");
+    // structure the kernel relies on (what the reference's per-vector generators produce)
+    for (int t = 0; t < 9; ++t)
+        for (int o = 0; o < kNB; ++o) {
+            for (int ci = 1; ci < 3; ++ci)
+                if (!bits_equal(W->stripe[(t * 3 + ci) * kNB + o], W->stripe[(t * 3) * kNB + o]))
+                    return fail(SILENT_E_STRUCTURE, "stripe bank differs across input channels at tap %d", t);
+            for (int ci = 0; ci < kNB; ++ci)
+                if (ci != o && W->end[(t * kNB + ci) * kNB + o] != 0.0f)
+                    return fail(SILENT_E_STRUCTURE, "end bank couples orientations %d -> %d (needs a depthwise bank)", ci, o);
+        }
+    ParamsBank B;
+    float blur_min = INFINITY;
+    for (int t = 0; t < 49; ++t) {
+        for (int sl = 0; sl < kNB * kNB; ++sl)
+            if (!bits_equal(W->blur[t * kNB * kNB + sl], W->blur[t * kNB * kNB]))
+                return fail(SILENT_E_STRUCTURE, "blur bank slices differ at tap %d", t);
+        const float b = W->blur[t * kNB * kNB];
+        B.wb[t] = dup(b);
+        blur_min = b < blur_min ? b : blur_min;
+        if (!(b > 0.0f) || std::isinf(b)) blur_min = -1.0f;
+    }
+    for (int t = 0; t < 9; ++t)
+        for (int o = 0; o < kNB; ++o) {
+            B.w3[t][o] = dup(W->stripe[(t * 3) * kNB + o]);
+            B.w5[t][o] = dup(W->end[(t * kNB + o) * kNB + o]);
+        }
+    B.quick_thr = 0.0f;
+    if (blur_min > 0.0f && blur_min < INFINITY) {
+        float T = (float)(1.0001 / (double)blur_min);
+        for (int guard = 0; guard < 8 && !((double)blur_min * (double)T >= 1.0001); ++guard) T = std::nextafterf(T, INFINITY);
+        if ((double)blur_min * (double)T >= 1.0001 && T < 1.0e20f) B.quick_thr = T;
+    }
+    B.reg_value = W->regulation_value, B.reg_root = W->regulation_root, B.clip_max = W->clip_max, B.border = W->border;
+    B.h = h, B.w = w, B.n = n, B.pair_levels = pair_levels;
+
+    // S1 + S2 -> channel sum, exactly as in the three-orientation pipeline
+    silent_stack_weights tmp;
+    std::memset(&tmp, 0, sizeof(tmp));
+    std::memcpy(tmp.rgc, W->rgc, sizeof(tmp.rgc));
+    std::memcpy(tmp.rgby, W->rgby, sizeof(tmp.rgby));
+    for (float &b : tmp.blur) b = 1.0f;
+    tmp.regulation_value = 1.0f, tmp.regulation_root = 0.1f, tmp.clip_max = W->clip_max, tmp.border = W->border;
+    StackPlanHost S;
+    int rc = pack_stack_params(&tmp, n, h, w, &S);
+    if (rc != SILENT_OK) return rc;
+    S.a.pair_levels = pair_levels;
+    f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    rc = pick_tile_w(w) == 48 ? launch_stack_a<48>(xpair, S, true, pairs, bsum2, stream)
+                              : launch_stack_a<64>(xpair, S, true, pairs, bsum2, stream);
+    if (rc != SILENT_OK) return rc;
+
+    using T = TileBank<kBankTH, kBankTW>;
+    constexpr int NT = (T::CS_ROWS * T::C_RUNS + 31) / 32 * 32;
+    auto kern = stack_bank_kernel<kBankTH, kBankTW, NT>;
+    SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
+    const dim3 grid(ceil_div(w, kBankTW), ceil_div(h, kBankTH), pairs);
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), T::kSmemBytes, stream, (const f2 *)bsum2, B, orient, line_end, gray));
+    SILENT_LAUNCH_CHECK("stack_bank_kernel");
+    return SILENT_OK;
+}
 }  // namespace silent
 
 extern "C" {

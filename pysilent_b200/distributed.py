@@ -128,6 +128,7 @@ class PointGather:
         self.recv = [torch.zeros((self.world, rows, 4), dtype=torch.int64, device=self.device) for _ in range(depth)]
         self.packed = [torch.cuda.Event() for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.work = [None] * depth      # the collective's Work handle: result() asks it for asynchronous NCCL errors
         self.submitted = 0
 
     def submit(self, points, count, frame_offset):
@@ -148,12 +149,25 @@ class PointGather:
             if self.world == 1:
                 self.recv[k][0].copy_(self.send[k], non_blocking=True)
             else:
-                dist.all_gather_into_tensor(self.recv[k].view(-1, 4), self.send[k], group=self.group)
+                self.work[k] = dist.all_gather_into_tensor(self.recv[k].view(-1, 4), self.send[k], group=self.group,
+                                                           async_op=True)
+                self.work[k].wait()     # orders the side stream behind the collective; does not block the host
             self.done[k].record(self.side)
         return k
 
     def result(self, slot):
         self.done[slot].synchronize()
+        work = self.work[slot]
+        if work is not None:
+            # NCCL reports failures of an already enqueued collective asynchronously (a peer died, the communicator was
+            # aborted, the watchdog timed out): surface them here instead of handing out a half-filled buffer
+            work.wait()
+            err = work.exception() if hasattr(work, "exception") else None
+            if err is not None:
+                raise RuntimeError("feature-point all-gather failed: %s" % (err,))
+            counts_ok = self.recv[slot][:, self.capacity, 1:].abs().sum().item() == 0   # the count row is (count, 0, 0, 0)
+            if not counts_ok:
+                raise RuntimeError("feature-point all-gather delivered a malformed count row")
         recv = self.recv[slot]
         counts = recv[:, self.capacity, 0].clone()
         host = counts.tolist()

@@ -53,6 +53,7 @@ class LineEndPipeline:
                  orientations=None):
         self.orientations = orientations   # None: the reference's 3 simplex orientations (fused kernels); n: config C4
         self._bank = None
+        self._bank_weights = None
         self.output_size = tuple(output_size)
         self.output_colors = output_colors
         self.zoom_ratio = zoom_ratio
@@ -167,8 +168,11 @@ class LineEndPipeline:
         """
         frames = frames if frames.dim() == 4 else frames.unsqueeze(0)
         frames = frames.contiguous()
-        if self.orientations is not None:   # C4: pyramid kernel, then the orientation bank operator by operator
-            from .util.zoom.from_image import image_to_zoom_tensor
+        if self.orientations is not None:   # config C4
+            if self.orientations == 8 and frames.dtype == torch.uint8 and frames.shape[3] >= 3 and self.blur_size == 7 \
+                    and self.output_colors == 3 and (frames.shape[2] * frames.shape[3]) % 16 == 0:
+                return self._run_frames_bank(frames, want_points, points_capacity)   # fused: 4 kernels + emit
+            from .util.zoom.from_image import image_to_zoom_tensor   # any other bank: operator by operator
             return self.run_bank(image_to_zoom_tensor(frames, self.output_colors, self.output_size, self.zoom_ratio),
                                  want_points)
         plan = self.plan_for(frames)
@@ -197,6 +201,33 @@ class LineEndPipeline:
         total = int(count.item())
         if total > cap:   # rare (e.g. an all-black level emits every pixel): redo the emit with room for everything
             return self.run_frames(frames, want_points, points_capacity=total)
+        return LineEndResult(orient, line_end, None, points[:total])
+
+    def _run_frames_bank(self, frames, want_points=True, points_capacity=None):
+        """Config C4 fused: pyramid_pair_kernel -> stack_a (rgc, rgby) -> stack_bank_kernel (8-orientation stripe bank,
+        regulator, depthwise end bank, mask, mean) -> emit, through ``silent_pipeline_run_bank``."""
+        plan = self.plan_for(frames)
+        b = int(frames.shape[0])
+        plan.reserve(b)
+        n, dev = b * plan.levels, frames.device
+        if self._bank_weights is None:
+            f = self.bank_filters()
+            self._bank_weights = _lib.make_bank_weights(f["rgc"], f["rgby"], f["stripe"], f["blur"], f["end"])
+        orient = torch.empty((n, plan.h, plan.w, 8), dtype=torch.float32, device=dev)
+        line_end = torch.empty_like(orient)
+        cap = int(points_capacity) if points_capacity else max(64 * n, 1024)
+        points = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().silent_pipeline_run_bank(
+                plan.handle, ctypes.byref(self._bank_weights), _ops.ptr(frames), b, _ops.ptr(orient), _ops.ptr(line_end),
+                _ops.ptr(points), cap, _ops.ptr(count) if want_points else None, _ops.stream_ptr()),
+                "silent_pipeline_run_bank")
+        if not want_points:
+            return LineEndResult(orient, line_end, None, None)
+        total = int(count.item())
+        if total > cap:
+            return self._run_frames_bank(frames, want_points, points_capacity=total)
         return LineEndResult(orient, line_end, None, points[:total])
 
     # -- host buffers on both sides (LineEndDisplayer.callback) -----------------------------------------------------------

@@ -37,6 +37,12 @@ class LineEndDisplayer(LineEndPipeline):
         self.centroid_region_shape = [1, 3, 3]  # 2 or 3 are good values for this
         self.pyramid_tensor_shape = None
         self.energy_values = None
+        # page-locked host buffers of callback(): a ring of `host_slots` sets, so the arrays handed out by one call stay
+        # untouched for the next host_slots - 1 calls (the reference returns fresh arrays; a consumer that keeps frames
+        # longer copies them)
+        self.host_slots = 3
+        self._slot = -1
+        self._pinned = {}
 
     # -- the part of compile() after gray_line_end_tensor (recognition_testing.py:79-100) -------------------------------
     def display_tensors(self, orient, padded_line_end, gray=None):
@@ -72,9 +78,29 @@ class LineEndDisplayer(LineEndPipeline):
     def callback(self, frame, cam_id=None, depth=2):
         """``recognition_testing.py:136-144``: ``[frame] + [[tensors[x][y] for y in levels] for x in range(6)]``."""
         z = np.asarray(frame)
-        dev = torch.from_numpy(np.ascontiguousarray(z if z.dtype == np.uint8 else z.astype(np.float32)))
-        tensors = [t.cpu().numpy() for t in self.run_frames_display(dev.to(self._device()))]
-        return [frame] + [[tensors[x][y] for y in range(len(tensors[x]))] for x in range(6)]
+        z = np.ascontiguousarray(z if z.dtype == np.uint8 else z.astype(np.float32))
+        dev = self._device()
+        self._slot = (self._slot + 1) % self.host_slots
+        # frame in through a page-locked buffer (asynchronous H2D), the six tensors out into page-locked buffers with
+        # asynchronous copies and ONE synchronisation -- instead of a pageable upload and six blocking .cpu() calls
+        staged = self._host_buffer(("frame", self._slot), z.shape, torch.uint8 if z.dtype == np.uint8 else torch.float32)
+        staged.numpy()[...] = z
+        with torch.cuda.device(dev):
+            tensors = self.run_frames_display(staged.to(dev, non_blocking=True).unsqueeze(0))
+            outs = []
+            for i, t in enumerate(tensors):
+                host = self._host_buffer(("out", self._slot, i), tuple(t.shape), t.dtype)
+                host.copy_(t, non_blocking=True)
+                outs.append(host.numpy())
+            torch.cuda.current_stream().synchronize()
+        return [frame] + [[outs[x][y] for y in range(len(outs[x]))] for x in range(6)]
+
+    def _host_buffer(self, key, shape, dtype):
+        buf = self._pinned.get(key)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self._pinned[key] = buf
+        return buf
 
     def display(self, frame, cam_id=None):
         """``PyramidDisplayer.display`` (``pyramid_displayer.py:35-40``): everything scaled by 1/255 for the windows."""

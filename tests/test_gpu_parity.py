@@ -404,14 +404,10 @@ def test_fused_stack_routes_non_finite_input(c_oracle, default_filters):
 
 # ---- BASELINE config C4: 8-orientation bank, 8-level 4K pyramid ----------------------------------------------------------
 
-def _oracle_bank(c_oracle, pyr, f, region):
-    a = c_oracle.conv2d(c_oracle.conv2d(pyr, f["rgc"], post=1), f["rgby"], post=1)
-    orient = c_oracle.regulate_tensor(c_oracle.conv2d(a, f["stripe"], post=1), f["blur"], 1.0, .1)
-    line_end = c_oracle.conv2d(orient, f["end"], post=2, clip_hi=255.0)
-    padded = c_oracle.pad_inwards(line_end, [[0, 0], [2, 2], [2, 2], [0, 0]])
-    gray = c_oracle.get_value_from_color(padded)
-    points, _ = c_oracle.max_value_indices_region(gray, region)
-    return dict(orient=orient, padded=padded, gray=gray, points=points)
+def _oracle_bank(c_oracle, pyr, f, region, order="fused"):
+    """uint8 frames take the fused bank path (rgc / rgby in the fused order); ``run_bank`` on a pyramid goes operator by
+    operator."""
+    return c_oracle.bank_stack(pyr, f, region, order=order)
 
 
 def test_orientation_bank_config4_bit_exact(c_oracle, goldens):
@@ -424,12 +420,14 @@ def test_orientation_bank_config4_bit_exact(c_oracle, goldens):
     G = goldens["generators"]
     assert np.array_equal(f["stripe"], G["stripe_8"][:, :, :3, :]) and np.array_equal(f["end"], G["end_8"])
     assert np.array_equal(f["blur"], G["blur_8"])
-    frames = np.stack([structured_frame(70 + i, 300, 420) for i in range(2)])
+    frames = np.stack([structured_frame(70 + i, 300, 432) for i in range(3)])   # odd batch: a lone frame in the last pair
     pyr = c_oracle.from_image(frames, 3, (96, 64), 2 ** .5)
     ref = _oracle_bank(c_oracle, pyr, f, (32, 48))
     res = pipe.run_frames(torch.from_numpy(frames).cuda())
     assert tuple(res.orient.shape) == pyr.shape[:3] + (8,)
     _check_stack(res, ref, None, "config 4 bank")
+    per_op = pipe.run_bank(pyr)   # the same bank operator by operator (any channel count / structure)
+    _check_stack(per_op, _oracle_bank(c_oracle, pyr, f, (32, 48), order="operator"), None, "config 4 bank, per operator")
     lit_orient = lit.regulate_tensor(lit.conv_relu(lit.conv_relu(lit.conv_relu(pyr, f["rgc"]), f["rgby"]), f["stripe"]),
                                      f["blur"], 1.0, .1)
     assert_close(res.orient, lit_orient, "config 4 orient literal", tol=2e-5)
