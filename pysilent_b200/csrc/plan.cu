@@ -202,7 +202,7 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
         double best = -1.0;
         pl.th = 1;
         for (int th = 1; th <= 48; ++th) {   // (16 was measured 3 % slower: taller tiles amortise the per-tile set-up)
-            if ((size_t)th * pl.vpitch * 8 > 72 * 1024 && th > 1) break;
+            if ((size_t)th * pl.vpitch * 8 > (size_t)72 * 1024 * kPairThreads / 256 && th > 1) break;   // 768 threads per SM
             const int tasks = th * groups, rounds = ceil_div(tasks, kPairThreads);
             const double fill = (double)tasks / ((double)kPairThreads * rounds) + 0.002 * th;   // prefer taller tiles on ties
             if (fill > best) best = fill, pl.th = th;

@@ -150,7 +150,7 @@ __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t selector)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, selector));
 }
 
-__global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __grid_constant__ PairParams P)
+__global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair_kernel(const __grid_constant__ PairParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     f2 *sV = reinterpret_cast<f2 *>(smem_raw);                          // [th][vpitch] column sums (frame A, frame B)
@@ -239,29 +239,31 @@ __global__ void __launch_bounds__(kPairThreads, 3) pyramid_pair_kernel(const __g
     //      (192 of the 256 threads work here.)
     // Lanes interleave (column, channel): three consecutive lanes read three consecutive column sums (the B, G, R bytes
     // of one source pixel), so a warp's gather touches a third of the 128-byte lines it would with one channel per warp.
-    const int c = tid % 3;
-    const int ox = bx * P.tile_w + tid / 3;
-    if (tid >= 3 * P.tile_w || ox >= w) return;
-    const int32_t *tx = idx_x + (size_t)ox * kTaps;
-    const bool col_ok = __ldg(tx) >= 0;
-    int off[kTaps];
-    f2 wx[kTaps];
-#pragma unroll
-    for (int i = 0; i < kTaps; ++i) {
-        const int b = col_ok ? __ldg(tx + i) * P.FC - 4 * wlo + c : 0;
-        off[i] = b + (kVGroup - 16) * (b >> 4);   // position in the padded column-sum row
-        const float v = col_ok ? __ldg(w_x + (size_t)ox * kTaps + i) : 0.0f;
-        wx[i] = make_float2(v, v);
-    }
     const size_t plane = (size_t)h * w;
-    f2 *out = P.xpair + (((size_t)q * P.L + level) * 3 + c) * plane + (size_t)oy0 * w + ox;
     const int rows = min(th, h - oy0);
-    for (int r = 0; r < rows; ++r) {
-        const f2 *row = sV + (size_t)r * vpitch;
-        f2 acc = make_float2(0.0f, 0.0f);
+    for (int item = tid; item < 3 * P.tile_w; item += kPairThreads) {   // one pass when the CTA has >= 3 * tile_w threads
+        const int c = item % 3;
+        const int ox = bx * P.tile_w + item / 3;
+        if (ox >= w) break;
+        const int32_t *tx = idx_x + (size_t)ox * kTaps;
+        const bool col_ok = __ldg(tx) >= 0;
+        int off[kTaps];
+        f2 wx[kTaps];
 #pragma unroll
-        for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[off[i]], acc);   // zero weights when !col_ok
-        out[(size_t)r * w] = acc;
+        for (int i = 0; i < kTaps; ++i) {
+            const int b = col_ok ? __ldg(tx + i) * P.FC - 4 * wlo + c : 0;
+            off[i] = b + (kVGroup - 16) * (b >> 4);   // position in the padded column-sum row
+            const float v = col_ok ? __ldg(w_x + (size_t)ox * kTaps + i) : 0.0f;
+            wx[i] = make_float2(v, v);
+        }
+        f2 *out = P.xpair + (((size_t)q * P.L + level) * 3 + c) * plane + (size_t)oy0 * w + ox;
+        for (int r = 0; r < rows; ++r) {
+            const f2 *row = sV + (size_t)r * vpitch;
+            f2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[off[i]], acc);   // zero weights when !col_ok
+            out[(size_t)r * w] = acc;
+        }
     }
 }
 

@@ -1650,7 +1650,12 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
     if (between_kernels) SILENT_CUDA(cudaEventRecord(between_kernels, stream));   // stage timing hook
     if (!(S.s3_sym && S.s5_ownoth))
         return launch_b<kTileHB, TW, false, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
-    if (!(S.b.quick_thr > 0.0f && tile_flag))
+    // a grid that fits the device in about one wave (single frames, config C2) gains nothing from the quick variant's
+    // higher occupancy and would pay for a second launch: the full variant does it alone
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
+    if (!(S.b.quick_thr > 0.0f && tile_flag) || tiles <= 3LL * sms)
         return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
     // quick variant on every tile, then the full variant on the tiles it flagged (none on textured input)
     const size_t flags = (size_t)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);

@@ -161,10 +161,9 @@ class PointGather:
         if work is not None:
             # NCCL reports failures of an already enqueued collective asynchronously (a peer died, the communicator was
             # aborted, the watchdog timed out): surface them here instead of handing out a half-filled buffer
-            work.wait()
-            err = work.exception() if hasattr(work, "exception") else None
-            if err is not None:
-                raise RuntimeError("feature-point all-gather failed: %s" % (err,))
+            work.wait()                     # raises the NCCL error, if any (torch's async error handling)
+            if not work.is_completed():
+                raise RuntimeError("feature-point all-gather did not complete")
             counts_ok = self.recv[slot][:, self.capacity, 1:].abs().sum().item() == 0   # the count row is (count, 0, 0, 0)
             if not counts_ok:
                 raise RuntimeError("feature-point all-gather delivered a malformed count row")
