@@ -14,12 +14,12 @@ struct LevelInfo {
 
 // Launch geometry of pyramid_pair_kernel for one level: x tiles of kPairTileW output columns; per tile the span of
 // aligned 32-bit words of a frame row that its x-taps touch.
-constexpr int kPairTileWMax = 85;   // phase H runs one thread per (column, channel): 3 * 85 <= 256 threads
+constexpr int kPairTileWMax = 85;   // phase H deals the (column, channel) items of a tile over the CTA's threads
 constexpr int kPairMaxTiles = 64, kPairMaxLevels = 16;
 #ifndef SILENT_PAIR_THREADS
-#define SILENT_PAIR_THREADS 256
+#define SILENT_PAIR_THREADS 128
 #endif
-constexpr int kPairThreads = SILENT_PAIR_THREADS;   // threads per CTA of pyramid_pair_kernel
+constexpr int kPairThreads = SILENT_PAIR_THREADS;   // threads per CTA of pyramid_pair_kernel (measured: 64 / 96 / 192 / 256 slower)
 struct PairLevel {
     int ntx = 0, th = 0, vpitch = 0;
     int word_lo[kPairMaxTiles], nwords[kPairMaxTiles];
