@@ -1113,7 +1113,7 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
 // small 1-D grid of CTAs walks the tile list and redoes the flagged tiles (none on textured input: the pass then costs
 // a few microseconds instead of a full grid of early exits).
 template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
-__global__ void __launch_bounds__(NT, LITE ? 3 : 2)
+__global__ void __launch_bounds__(NT, LITE ? (TH <= 12 ? 5 : TH <= 16 ? 4 : 3) : 2)
 stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, const __grid_constant__ CUtensorMap tmap,
                float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
                int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs)
@@ -1549,7 +1549,7 @@ int pack_stack_params(const silent_stack_weights *W, int n, int h, int w, StackP
 }
 
 #ifndef SILENT_TILE_HB
-#define SILENT_TILE_HB 24
+#define SILENT_TILE_HB 16
 #endif
 #ifndef SILENT_TILE_HA
 #define SILENT_TILE_HA 16

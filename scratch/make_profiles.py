@@ -36,7 +36,7 @@ with open('profiles/%s_ncu_full_summary.csv' % tag, 'w', newline='') as f:
         def mb(metric):
             v = float(r[hdr.index(metric)].replace(',', '')); u = units[hdr.index(metric)]
             return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
-        traffic[short] = int(mb('dram__bytes_read.sum') + mb('dram__bytes_write.sum'))
+        traffic[short] = traffic.get(short, 0) + int(mb('dram__bytes_read.sum') + mb('dram__bytes_write.sum'))   # (variants add up)
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 blocks = []
 for r in csv.reader(io.StringIO(src)):
