@@ -588,7 +588,11 @@ struct TileB {
     // 7 rows x 3 quads instead of 7 x 14 values. Two spare quads per row (never computed, always "large").
     static constexpr int Q_PITCH = round_pitch(2 * C_RUNS + 2);
     static constexpr int Q_PLANE = CS_ROWS * Q_PITCH;
-    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE + Q_PLANE) * sizeof(f2) + 64;
+    // the quad sums die with S4, before the staging buffer is first written: they live in the part of the front region
+    // the input planes leave free when there is room (quick variant, 16-row tiles: 44 KB per CTA, 5 CTAs per SM)
+    static constexpr bool Q_IN_FRONT = B_PLANE + CS_PLANE + Q_PLANE <= FRONT_F2;
+    static constexpr int Q_OFFSET = Q_IN_FRONT ? B_PLANE + CS_PLANE : FRONT_F2 + 3 * CD_PLANE;
+    static constexpr size_t kSmemBytes = (size_t)(FRONT_F2 + 3 * CD_PLANE + (Q_IN_FRONT ? 0 : Q_PLANE) + 8) * sizeof(f2) + 64;
     static_assert(TW % kPX == 0, "tile width must be a multiple of the run length");
 };
 
@@ -614,9 +618,9 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     f2 *sB = reinterpret_cast<f2 *>(smem_raw);   // [B_ROWS][B_PITCH]       rgby channel sum, origin (-5, -5)
     f2 *sCs = sB + T::B_PLANE;                   // [CS_ROWS][CS_PITCH]     stripe channel sum, origin (-4, -4)
     f2 *sCD = sB + T::FRONT_F2;                  // [3][CD_ROWS][CD_PITCH]  stripe, regulated in place, origin (-1, -1)
-    f2 *sQ = sCD + 3 * T::CD_PLANE;              // [CS_ROWS][Q_PITCH]      quad maxima of sCs, origin (-4, -4)
+    f2 *sQ = sB + T::Q_OFFSET;                   // [CS_ROWS][Q_PITCH]      quad sums of the stripe sum, origin (-4, -4)
     float *sStage = reinterpret_cast<float *>(sB);   // [2][TH][ST_PITCH] NHWC staging, valid after the S4 barrier
-    int *sWin = reinterpret_cast<int *>(sQ + T::Q_PLANE);   // [2 images][4 windows] + [2 images] tile maxima
+    int *sWin = reinterpret_cast<int *>(sB + T::FRONT_F2 + 3 * T::CD_PLANE + (T::Q_IN_FRONT ? 0 : T::Q_PLANE));   // 10 ints
     float *sGray = reinterpret_cast<float *>(sCD);                // [2][TH][G_PITCH] gray staging, valid after the S5 barrier
 
     const int tid = threadIdx.x;
@@ -899,7 +903,7 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     //      the end filter at once; the copy drains while S5 computes ---------------------------------------------
     const bool bulk_ok = (w % 4) == 0;   // staged rows start and end on 16-byte boundaries of the global tensors
     constexpr int kS5Warps = (TH * T::E_RUNS + 31) / 32, kIdleWarps = NT / 32 - kS5Warps;
-    constexpr bool kSideRestage = kIdleWarps >= 2;
+    constexpr bool kSideRestage = kIdleWarps >= 1;   // (16-row tiles: 3 warps run S5, the 4th restages and stores orient)
     constexpr int kRestageFirst = kSideRestage ? 32 * kS5Warps : 0, kRestageThreads = kSideRestage ? 32 * kIdleWarps : NT;
     bool issued_orient = false, issued_line_end = false;
     if (orient && tid >= kRestageFirst) {
@@ -1113,7 +1117,7 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
 // small 1-D grid of CTAs walks the tile list and redoes the flagged tiles (none on textured input: the pass then costs
 // a few microseconds instead of a full grid of early exits).
 template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
-__global__ void __launch_bounds__(NT, LITE ? (TH <= 12 ? 5 : TH <= 16 ? 4 : 3) : 2)
+__global__ void __launch_bounds__(NT, LITE ? (TH <= 16 ? 5 : 3) : 2)
 stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, const __grid_constant__ CUtensorMap tmap,
                float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
                int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs)
