@@ -214,30 +214,52 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
     for (int t = tid; t < ntiles; t += 256)
         s_flag[t] = tile_is_candidate(tm, level_tiles, t / tm.ntx, t % tm.ntx, h, w, g, level_pool);
     __syncthreads();
+    // compact list of the flagged tiles (order is irrelevant for counting), then ONE flat loop over (flagged tile, quad):
+    // a thread's loads are independent of each other, so the level costs about one memory round trip however many tiles
+    // are flagged (a loop per tile cost one round trip per flagged tile)
+    __shared__ int s_list[kEmitMaxTiles];
+    __shared__ int s_nflag;
+    if (tid == 0) s_nflag = 0;
+    __syncthreads();
+    for (int t = tid; t < ntiles; t += 256)
+        if (s_flag[t]) s_list[atomicAdd(&s_nflag, 1)] = t;
+    __syncthreads();
     const int quads = (tm.tile_w + 3) >> 2;
     const bool vec_ok = (w & 3) == 0 && (tm.tile_w & 3) == 0;
-    for (int t = 0; t < ntiles; ++t) {
-        if (!s_flag[t]) continue;   // (uniform)
-        const int ty = t / tm.ntx, tx = t - ty * tm.ntx;
-        const int x0 = tx * tm.tile_w, y0 = ty * tm.tile_h;
-        const int rows = min(tm.tile_h, h - y0);
-        for (int i = tid; i < rows * quads; i += 256) {
-            const int r = i / quads, x = x0 + 4 * (i - r * quads), y = y0 + r;
-            const float *pool_row = level_pool + nearest_src(y, g.sy, g.oh) * g.ow;
-            float f[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
-            if (vec_ok && x + 4 <= w) {
-                const float4 q = __ldg(reinterpret_cast<const float4 *>(v + (size_t)y * w + x));
-                f[0] = q.x, f[1] = q.y, f[2] = q.z, f[3] = q.w;
-            } else {
+    const int per_tile = tm.tile_h * quads, items = s_nflag * per_tile;
+    for (int i0 = tid; i0 < items; i0 += 4 * 256) {
+        float4 q[4];
+        int xs[4], ys[4], xe[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (x + e < min(w, x0 + tm.tile_w)) f[e] = __ldg(v + (size_t)y * w + x + e);
+        for (int u = 0; u < 4; ++u) {   // up to four independent 128-bit loads in flight per thread
+            const int i = i0 + u * 256;
+            ys[u] = -1;
+            if (i >= items) continue;
+            const int t = s_list[i / per_tile], rest = i % per_tile;
+            const int ty = t / tm.ntx, tx = t - ty * tm.ntx;
+            const int r = rest / quads, x = tx * tm.tile_w + 4 * (rest - r * quads), y = ty * tm.tile_h + r;
+            if (y >= h || x >= w) continue;
+            ys[u] = y, xs[u] = x, xe[u] = min(w, tx * tm.tile_w + tm.tile_w);
+            const float *src = v + (size_t)y * w + x;
+            if (vec_ok && x + 4 <= w) {
+                q[u] = __ldg(reinterpret_cast<const float4 *>(src));
+            } else {
+                q[u].x = __ldg(src);
+                q[u].y = x + 1 < xe[u] ? __ldg(src + 1) : -1.0f;
+                q[u].z = x + 2 < xe[u] ? __ldg(src + 2) : -1.0f;
+                q[u].w = x + 3 < xe[u] ? __ldg(src + 3) : -1.0f;
             }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (ys[u] < 0) continue;
+            const float *pool_row = level_pool + nearest_src(ys[u], g.sy, g.oh) * g.ow;
+            const float f[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
             int hits = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (x + e < min(w, x0 + tm.tile_w)) hits += f[e] >= __ldg(pool_row + nearest_src(x + e, g.sx, g.ow));
-            if (hits) atomicAdd(&s_rows[y], hits);
+                if (xs[u] + e < xe[u]) hits += f[e] >= __ldg(pool_row + nearest_src(xs[u] + e, g.sx, g.ow));
+            if (hits) atomicAdd(&s_rows[ys[u]], hits);
         }
     }
     __syncthreads();

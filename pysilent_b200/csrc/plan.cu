@@ -173,6 +173,7 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
         const int waste = ceil_div(w, tw) * tw - w;
         if (waste <= best_waste) best_waste = waste, kPairTileW = tw;
     }
+    if (const char *e = std::getenv("SILENT_PAIR_TILEW")) kPairTileW = std::max(8, std::min(kPairTileWMax, std::atoi(e)));   // tuning knob
     plan->pair_tile_w = kPairTileW;
     plan->pair_ok = L > 0 && L <= kPairMaxLevels && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3;
     for (int s = 0; s < L && plan->pair_ok; ++s) {

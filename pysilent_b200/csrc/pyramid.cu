@@ -203,9 +203,10 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     for (int t = tid; t < th * nq; t += kPairThreads) {
         const int r = t / nq, qi = t - r * nq;
         f2 acc[16];
+        if (sTy[r * kTaps] < 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
-        if (sTy[r * kTaps] >= 0) {
+            for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
+        } else {
             uint4 qa[kTaps], qb[kTaps];
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
                 qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + off) + (wlo >> 2) + qi);
                 qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + off) + (wlo >> 2) + qi);
             }
+            // The first tap is a plain product: fma(w, v, +0) and w * v differ only when the product is -0 (a negative
+            // weight on a zero byte), and a -0 column sum cannot change any output bit (phase H adds every term to +0).
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
                 const float wy = sWy[r * kTaps + j];
@@ -220,10 +223,11 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
                 const uint32_t wa[4] = {qa[j].x, qa[j].y, qa[j].z, qa[j].w}, wb[4] = {qb[j].x, qb[j].y, qb[j].z, qb[j].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    acc[4 * k + 0] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7440), magic_byte(wb[k], 0x7440)), bias), acc[4 * k + 0]);
-                    acc[4 * k + 1] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7441), magic_byte(wb[k], 0x7441)), bias), acc[4 * k + 1]);
-                    acc[4 * k + 2] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7442), magic_byte(wb[k], 0x7442)), bias), acc[4 * k + 2]);
-                    acc[4 * k + 3] = __ffma2_rn(wy2, __fadd2_rn(make_float2(magic_byte(wa[k], 0x7443), magic_byte(wb[k], 0x7443)), bias), acc[4 * k + 3]);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const f2 v = __fadd2_rn(make_float2(magic_byte(wa[k], 0x7440 + b), magic_byte(wb[k], 0x7440 + b)), bias);
+                        acc[4 * k + b] = j == 0 ? __fmul2_rn(wy2, v) : __ffma2_rn(wy2, v, acc[4 * k + b]);
+                    }
                 }
             }
         }
