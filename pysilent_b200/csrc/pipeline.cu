@@ -79,6 +79,7 @@ silent_plan::~silent_plan()
     release(ws);
     if (d_tables) cudaFree(d_tables);
     if (d_pair_words) cudaFree(d_pair_words);
+    if (d_pair_htab) cudaFree(d_pair_htab);
 }
 
 extern "C" {

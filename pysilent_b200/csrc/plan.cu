@@ -246,6 +246,28 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 e = cudaMalloc(&plan->d_pair_words, words.size() * sizeof(int));
                 if (e == cudaSuccess)
                     e = cudaMemcpy(plan->d_pair_words, words.data(), words.size() * sizeof(int), cudaMemcpyHostToDevice);
+                // phase-H table: per (level, output column, channel) the six positions of its taps in a padded column-sum
+                // row -- up to the tile's own origin, which is a constant the kernel subtracts -- and the six weights
+                // (zero for columns the reference leaves undefined). position(B) = B + 2 * (B >> 4) for the absolute byte
+                // column B = tap * frame_c + channel; tiles start at multiples of 16 bytes, so the shift distributes.
+                std::vector<int32_t> htab((size_t)L * w * 3 * 12, 0);
+                for (int s = 0; s < L; ++s)
+                    for (int ox = 0; ox < w; ++ox) {
+                        const int32_t *tx = &plan->idx_x[((size_t)s * w + ox) * kTaps];
+                        const float *gx = &plan->w_x[((size_t)s * w + ox) * kTaps];
+                        for (int c = 0; c < 3; ++c) {
+                            int32_t *row = &htab[(((size_t)s * w + ox) * 3 + c) * 12];
+                            for (int i = 0; i < kTaps; ++i) {
+                                const int B = tx[0] >= 0 ? tx[i] * p->frame_c + c : -1;
+                                row[i] = B >= 0 ? B + (kPairVGroup - 16) * (B >> 4) : -1;
+                                const float wv = tx[0] >= 0 ? gx[i] : 0.0f;
+                                std::memcpy(&row[6 + i], &wv, 4);
+                            }
+                        }
+                    }
+                if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_htab, htab.size() * sizeof(int32_t));
+                if (e == cudaSuccess)
+                    e = cudaMemcpy(plan->d_pair_htab, htab.data(), htab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) {
                     delete plan;
                     return fail(SILENT_E_CUDA, "upload of pyramid tile spans failed: %s", cudaGetErrorString(e));

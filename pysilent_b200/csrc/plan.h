@@ -19,6 +19,7 @@ constexpr int kPairMaxTiles = 64, kPairMaxLevels = 16;
 #ifndef SILENT_PAIR_THREADS
 #define SILENT_PAIR_THREADS 128
 #endif
+constexpr int kPairVGroup = 18;   // float2 slots per group of 16 byte-columns in the column-sum buffer (16 + 2 of padding)
 constexpr int kPairThreads = SILENT_PAIR_THREADS;   // threads per CTA of pyramid_pair_kernel (measured: 64 / 96 / 192 / 256 slower)
 struct PairLevel {
     int ntx = 0, th = 0, vpitch = 0;
@@ -68,6 +69,7 @@ struct silent_plan {
     bool pair_ok = false;
     int pair_tile_w = 64;                  // output columns per tile of the frame-pair pyramid kernel (see plan.cu)
     int *d_pair_words = nullptr;           // [L][kPairMaxTiles][2]: (word_lo, nwords) per level and x tile
+    int32_t *d_pair_htab = nullptr;        // [L][w][3][12]: phase-H tap positions (6 ints) and weights (6 floats), see plan.cu
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;

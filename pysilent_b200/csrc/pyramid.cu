@@ -127,7 +127,7 @@ int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, fl
 // ---------------------------------------------------------------------------------------------------------------------
 
 typedef float2 f2;
-constexpr int kVGroup = 18;   // float2 slots per group of 16 byte-columns in the column-sum buffer (16 + 2 of padding)
+constexpr int kVGroup = kPairVGroup;   // float2 slots per group of 16 byte-columns in the column-sum buffer (plan.h)
 
 struct PairParams {
     const uint8_t *frames;
@@ -135,6 +135,7 @@ struct PairParams {
     const int32_t *idx_y, *idx_x;   // tap tables of all levels: [L][h][6], [L][w][6]
     const float *w_y, *w_x;
     const int *words;               // [L][kPairMaxTiles][2]: first 32-bit word of a frame row and word count per x tile
+    const int32_t *htab;            // [L][w][3][12]: phase-H tap positions and weights (plan.cu)
     int H, row_bytes, FC;           // frame rows, bytes per frame row, interleaved channels
     int h, w, L, B, ntx, tile_w;
     // ONE launch covers every level: blockIdx.x enumerates the tiles of a frame pair with the COARSEST level first (it
@@ -162,8 +163,8 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     const int level = P.L - 1 - k, local = blockIdx.x - P.tile_start[k];
     const int bx = local % P.ntx, by = local / P.ntx, q = blockIdx.y;
     const int th = P.th[level], vpitch = P.vpitch[level], h = P.h, w = P.w;
-    const int32_t *idx_y = P.idx_y + (size_t)level * h * kTaps, *idx_x = P.idx_x + (size_t)level * w * kTaps;
-    const float *w_y = P.w_y + (size_t)level * h * kTaps, *w_x = P.w_x + (size_t)level * w * kTaps;
+    const int32_t *idx_y = P.idx_y + (size_t)level * h * kTaps;
+    const float *w_y = P.w_y + (size_t)level * h * kTaps;
     const int oy0 = by * th;
     int *sTy = reinterpret_cast<int *>(sV + (size_t)th * vpitch);   // [th][6] source rows (-1: row is zero)
     float *sWy = reinterpret_cast<float *>(sTy + th * kTaps);       // [th][6]
@@ -249,16 +250,21 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
         const int c = item % 3;
         const int ox = bx * P.tile_w + item / 3;
         if (ox >= w) break;
-        const int32_t *tx = idx_x + (size_t)ox * kTaps;
-        const bool col_ok = __ldg(tx) >= 0;
+        // six tap positions + six weights of this (column, channel): three 128-bit loads of a table that already holds the
+        // padded positions up to the tile origin (the per-tap index arithmetic and twelve scalar loads it replaces were
+        // 12 % of the kernel's instructions with 3-row tiles)
+        const int4 *tab = reinterpret_cast<const int4 *>(P.htab + ((((size_t)level * w + ox) * 3 + c) * 12));
+        const int4 t0 = __ldg(tab), t1 = __ldg(tab + 1), t2 = __ldg(tab + 2);
+        const int pos[kTaps] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y};
+        const float wv[kTaps] = {__int_as_float(t1.z), __int_as_float(t1.w), __int_as_float(t2.x),
+                                 __int_as_float(t2.y), __int_as_float(t2.z), __int_as_float(t2.w)};
+        const int origin = 4 * wlo + (kVGroup - 16) * (wlo >> 2);
         int off[kTaps];
         f2 wx[kTaps];
 #pragma unroll
         for (int i = 0; i < kTaps; ++i) {
-            const int b = col_ok ? __ldg(tx + i) * P.FC - 4 * wlo + c : 0;
-            off[i] = b + (kVGroup - 16) * (b >> 4);   // position in the padded column-sum row
-            const float v = col_ok ? __ldg(w_x + (size_t)ox * kTaps + i) : 0.0f;
-            wx[i] = make_float2(v, v);
+            off[i] = pos[0] >= 0 ? pos[i] - origin : 0;
+            wx[i] = make_float2(wv[i], wv[i]);
         }
         f2 *out = P.xpair + (((size_t)q * P.L + level) * 3 + c) * plane + (size_t)oy0 * w + ox;
         for (int r = 0; r < rows; ++r) {
@@ -299,6 +305,7 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     P.xpair = (f2 *)xpair_dev;
     P.idx_y = plan->d_idx_y, P.w_y = plan->d_w_y, P.idx_x = plan->d_idx_x, P.w_x = plan->d_w_x;
     P.words = plan->d_pair_words;
+    P.htab = plan->d_pair_htab;
     P.H = p.frame_h;
     P.row_bytes = p.frame_w * p.frame_c;
     P.FC = p.frame_c;
