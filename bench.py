@@ -349,8 +349,10 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    barrier()
+    # (started BEFORE the barrier: spawning nvidia-smi takes rank 0 about a millisecond, and a rank that enters the timed
+    # region late holds every other rank up through the point gather -- the max over ranks then measures the skew)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     launches0 = _lib.lib().silent_launch_count()
     ev0, ev1, ev_k = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     t_wall0 = time.perf_counter()
