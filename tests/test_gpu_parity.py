@@ -790,3 +790,21 @@ def test_pipeline_shape_sweep_bit_exact(c_oracle, default_filters):
         _check_stack(res, ref, None, "device %s" % (shape,))
         host = pipe.run_host(frames)
         _check_stack(host, ref, None, "host %s" % (shape,))
+
+
+def test_orientation_bank_shape_sweep_bit_exact(c_oracle):
+    """The fused bank path (config C4's kernels) around its tile boundaries: level widths that are (not) multiples of the
+    32-pixel tile / the 4-pixel run / 4 floats, level heights that are (not) multiples of 16, odd batches, frames with flat
+    and black patches (the regulator's slow path inside stack_bank_kernel). Values, NaN masks and points bit-equal to the
+    oracle's bank composition."""
+    from pysilent_b200 import LineEndPipeline
+    cases = [((120, 160), (72, 48), 1.3, 2), ((200, 304), (76, 52), 1.5, 3), ((333, 448), (144, 96), 1.25, 1),
+             ((480, 640), (100, 66), 1.7, 3), ((96, 128), (34, 18), 1.6, 5)]
+    for shape, center, scale, batch in cases:
+        frames = np.stack([structured_frame(60 + i, *shape) if i % 2 else synthetic_frame(9, i, *shape) for i in range(batch)])
+        pipe = LineEndPipeline(output_size=center, zoom_ratio=scale, orientations=8)
+        pyr = c_oracle.from_image(frames, 3, center, scale)
+        ref = _oracle_bank(c_oracle, pyr, pipe.bank_filters(), (center[1] // 2, center[0] // 2))
+        res = pipe.run_frames(torch.from_numpy(frames).cuda())
+        assert tuple(res.orient.shape) == pyr.shape[:3] + (8,)
+        _check_stack(res, ref, None, "bank %s" % (shape,))
