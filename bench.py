@@ -336,7 +336,7 @@ def run_ours(args, rank, local_rank, world):
     gather_cap = 8 * n   # rows per rank in the fixed-size all-gather (generic input: 1-4 points per level)
     # the path's only exchange: feature points to every rank over NCCL/NVLink, one all-gather per step on a side stream
     # (it overlaps the next step's kernels; the final barrier + synchronize below waits for the last one)
-    gatherer = sdist.PointGather(gather_cap, L, dev) if world > 1 else None
+    gatherer = sdist.PointGather(gather_cap, L, dev, native=args.native_gather) if world > 1 else None
 
     def step():
         pipe.run_frames(frames, out=bufs)
@@ -499,7 +499,9 @@ def run_ours(args, rank, local_rank, world):
                                          "all": rank_ms},
                   "host_enqueue_ms_per_step": {"max": max(enqueue_all), "all": enqueue_all},
                   "last_gather_wait_ms": {"max": max(wait_all), "all": wait_all},
-                  "gather_rows_per_rank": gather_cap + 1 if world > 1 else 0},
+                  "gather_rows_per_rank": gather_cap + 1 if world > 1 else 0,
+                  "gather_api": ("silent_gather_points (ncclAllGather)" if args.native_gather else
+                                 "torch.distributed.all_gather_into_tensor") if world > 1 else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic.get("dram_bytes_per_step") if traffic else None,
                      "kernel": "whole step per GPU: pyramid_pair_kernel + stack_a_kernel + stack_b_kernel (quick pass + "
@@ -554,6 +556,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1/C2/C4/C5 entries")
     ap.add_argument("--no-natural", dest="natural", action="store_false")
+    ap.add_argument("--native-gather", action="store_true",
+                    help="point gather through silent_gather_points (ncclAllGather behind the C ABI) instead of torch's")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -35,7 +35,8 @@ typedef enum silent_status {
     SILENT_E_SHAPE = -2,    /* shape / channel count / filter size not supported by this entry point */
     SILENT_E_CAPACITY = -3, /* plan workspace or caller buffer too small */
     SILENT_E_CUDA = -4,     /* CUDA runtime error (message has the cudaError string) */
-    SILENT_E_STRUCTURE = -5 /* weights lack the structure the fused stack needs; use the per-operator calls */
+    SILENT_E_STRUCTURE = -5, /* weights lack the structure the fused stack needs; use the per-operator calls */
+    SILENT_E_NCCL = -6       /* NCCL could not be loaded, or reported an error (also asynchronously) */
 } silent_status;
 
 typedef enum silent_dtype { SILENT_U8 = 0, SILENT_F32 = 1 } silent_dtype;
@@ -194,6 +195,21 @@ int silent_pointwise(const float *x_dev, const float *y_dev, size_t count, int k
  * counterpart (the reference is single-device, recognition_testing.py:64). */
 int silent_pack_points(const int64_t *points_dev, const int64_t *count_dev, int64_t capacity, int64_t level_offset,
                        int64_t *packed_dev, silent_stream stream);
+
+/* The gather itself, over NCCL/NVLink: every rank passes its packed block of `rows` (= capacity + 1) int64x4 rows;
+ * packed_recv_dev [nranks][rows][4] receives all blocks in rank order (= global frame order when ranks own contiguous
+ * frame blocks). One ncclAllGather on `stream` (asynchronous; use a side stream to overlap the next batch's kernels).
+ * NCCL is bound at run time (dlopen of the libnccl.so.2 already loaded in the process, e.g. PyTorch's, else the system's).
+ * Communicator set-up is the usual NCCL pattern: rank 0 calls silent_comm_unique_id (128 bytes), the host ships the id
+ * to every rank (any channel: torch.distributed, MPI, a file), every rank calls silent_comm_create on its own device.
+ * silent_gather_points and silent_comm_check report asynchronous NCCL errors of earlier collectives (SILENT_E_NCCL). */
+typedef struct silent_comm silent_comm;
+int silent_comm_unique_id(void *id_out_128_bytes);
+int silent_comm_create(const void *id_128_bytes, int nranks, int rank, silent_comm **out_comm);
+void silent_comm_destroy(silent_comm *comm);
+int silent_comm_check(silent_comm *comm);
+int silent_gather_points(silent_comm *comm, const int64_t *packed_send_dev, int64_t rows, int64_t *packed_recv_dev,
+                         silent_stream stream);
 
 /* ---- fused path ---------------------------------------------------------------------------------------------------- */
 

@@ -116,9 +116,13 @@ class PointGather:
     CUDA tensors + NCCL only (the gloo/CPU form is :func:`gather_points`).
     """
 
-    def __init__(self, capacity, levels_per_frame, device, group=None, depth=2):
+    def __init__(self, capacity, levels_per_frame, device, group=None, depth=2, native=False):
+        """``native``: issue the collective through the library's own entry point (``silent_gather_points``: one
+        ``ncclAllGather`` on the side stream, communicator created from an id that rank 0 broadcasts through
+        ``torch.distributed``) instead of ``torch.distributed.all_gather_into_tensor``."""
         from . import _lib, _ops
         self._lib, self._ops = _lib, _ops
+        self.comm = None
         self.capacity, self.levels, self.group = int(capacity), int(levels_per_frame), group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device(device)
@@ -130,6 +134,31 @@ class PointGather:
         self.done = [torch.cuda.Event() for _ in range(depth)]
         self.work = [None] * depth      # the collective's Work handle: result() asks it for asynchronous NCCL errors
         self.submitted = 0
+        if native and self.world > 1:
+            self.comm = self._create_native_comm(group)
+
+    def _create_native_comm(self, group):
+        import ctypes
+        rank = dist.get_rank(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            self._lib.check(self._lib.lib().silent_comm_unique_id(buf), "silent_comm_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(self.device) if on_gpu else ident
+        dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(ident.cpu().tolist())
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.lib().silent_comm_create(raw, self.world, rank, ctypes.byref(comm)),
+                            "silent_comm_create")
+        return comm
+
+    def close(self):
+        if self.comm is not None:
+            self._lib.lib().silent_comm_destroy(self.comm)
+            self.comm = None
 
     def submit(self, points, count, frame_offset):
         """points: int64 CUDA ``[>= capacity, 4]``, count: 1-element int64 CUDA tensor. Returns the slot index."""
@@ -148,6 +177,11 @@ class PointGather:
             self.side.wait_event(self.packed[k])
             if self.world == 1:
                 self.recv[k][0].copy_(self.send[k], non_blocking=True)
+            elif self.comm is not None:
+                with torch.cuda.device(self.device):
+                    self._lib.check(self._lib.lib().silent_gather_points(
+                        self.comm, self._ops.ptr(self.send[k]), self.capacity + 1, self._ops.ptr(self.recv[k]),
+                        self.side.cuda_stream), "silent_gather_points")
             else:
                 self.work[k] = dist.all_gather_into_tensor(self.recv[k].view(-1, 4), self.send[k], group=self.group,
                                                            async_op=True)
@@ -157,6 +191,8 @@ class PointGather:
 
     def result(self, slot):
         self.done[slot].synchronize()
+        if self.comm is not None:
+            self._lib.check(self._lib.lib().silent_comm_check(self.comm), "silent_comm_check")
         work = self.work[slot]
         if work is not None:
             # NCCL reports failures of an already enqueued collective asynchronously (a peer died, the communicator was

@@ -674,11 +674,13 @@ def _nccl_gather_worker(rank, world, port, out):
     L = res.orient.shape[0] // (hi - lo)
     pts = torch.zeros((256, 4), dtype=torch.int64, device="cuda")
     pts[: len(res.points)] = res.points
-    g = PointGather(256, L, torch.device("cuda", rank))
-    got = None
-    for _ in range(3):   # steady-state reuse of the slots
-        got, counts = g.result(g.submit(pts, torch.tensor([len(res.points)], device="cuda"), lo))
-    np.save(os.path.join(out, "nccl_%d.npy" % rank), got.cpu().numpy())
+    for native in (False, True):   # torch.distributed's collective, then the library's own silent_gather_points
+        g = PointGather(256, L, torch.device("cuda", rank), native=native)
+        got = None
+        for _ in range(3):   # steady-state reuse of the slots
+            got, counts = g.result(g.submit(pts, torch.tensor([len(res.points)], device="cuda"), lo))
+        np.save(os.path.join(out, "nccl_%d_%d.npy" % (rank, native)), got.cpu().numpy())
+        g.close()
     dist.destroy_process_group()
 
 
@@ -693,7 +695,8 @@ def test_point_gather_two_gpus_nccl(tmp_path):
     frames = np.stack([synthetic_frame(1, i, 480, 640) for i in range(5)])
     want = LineEndPipeline(zoom_ratio=1.3).run_frames(torch.from_numpy(frames).cuda()).points.cpu().numpy()
     for r in range(2):
-        assert np.array_equal(np.load(tmp_path / ("nccl_%d.npy" % r)), want)
+        for native in (0, 1):
+            assert np.array_equal(np.load(tmp_path / ("nccl_%d_%d.npy" % (r, native))), want), (r, native)
 
 
 def test_outputs_stay_inside_their_buffers():
