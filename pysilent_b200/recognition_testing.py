@@ -24,7 +24,8 @@ debug = True
 
 class LineEndDisplayer(LineEndPipeline):
     def __init__(self, n_dimensions=2, **argv):
-        """Mimics the blob cells in the lowest layer of the V1 in the neocortex (``recognition_testing.py:22-43``)."""
+        """Line-end ("end-stopped") detector stage on top of the pyramid pipeline; same constructor attributes as the
+        reference's ``LineEndDisplayer.__init__`` (``recognition_testing.py:22-43``)."""
         super(LineEndDisplayer, self).__init__(n_dimensions, **argv)
         self.tensor_return_type = [torch.Tensor]
         self.precompile_list = []
@@ -34,7 +35,7 @@ class LineEndDisplayer(LineEndPipeline):
         self.top_percent_pool = .5
         self.rotation_invariance = False
         self.padded_firing = None
-        self.centroid_region_shape = [1, 3, 3]  # 2 or 3 are good values for this
+        self.centroid_region_shape = [1, 3, 3]  # block size of the centroid / importance pooling (reference default)
         self.pyramid_tensor_shape = None
         self.energy_values = None
         # page-locked host buffers of callback(): a ring of `host_slots` sets, so the arrays handed out by one call stay
