@@ -294,14 +294,15 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
     __shared__ long long s_sum[8];
     const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool last = n == levels - 1;
-    // does this level write anything at all? (most CTAs leave here)
+    // points of the levels before this one (the last level also publishes the grand total); these loads and the row
+    // flags below are independent, so they share one memory round trip
+    long long sum = 0;
+    for (int k = tid; k < n; k += 256) sum += __ldg(level_total + k);
+    // does this level write anything at all?
     int any = 0;
     for (int y = tid; y < h; y += 256) any |= __ldg(row_offset + (size_t)n * h + y) & 0x40000000;
     any = __syncthreads_or(any) && capacity > 0;
     if (!any && !last) return;
-    // points of the levels before this one (the last level also publishes the grand total)
-    long long sum = 0;
-    for (int k = tid; k < n; k += 256) sum += __ldg(level_total + k);
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_sum[warp] = sum;
     __syncthreads();
@@ -317,8 +318,17 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
         const float *v = value + ((size_t)n * h + y) * w;
         const float *pool_row = level_pool + nearest_src(y, g.sy, g.oh) * g.ow;
         long long slot = before + (packed & 0x3fffffff);
+        // the row's tiles are tested by one lane each (their loads overlap), then only flagged tiles are walked in x order
+        unsigned flagged = 0;
+        for (int t0 = 0; t0 < tm.ntx; t0 += 32) {   // (levels wider than 32 tiles: the walk below re-tests beyond bit 31)
+            const int tx = t0 + lane;
+            const bool cand = tx < tm.ntx && tile_is_candidate(tm, level_tiles, y / tm.tile_h, tx, h, w, g, level_pool);
+            const unsigned b = __ballot_sync(0xffffffffu, cand);
+            if (t0 == 0) flagged = b;
+        }
         for (int tx = 0; tx < tm.ntx; ++tx) {
-            if (!tile_is_candidate(tm, level_tiles, y / tm.tile_h, tx, h, w, g, level_pool)) continue;
+            if (tx < 32 ? !((flagged >> tx) & 1u) : !tile_is_candidate(tm, level_tiles, y / tm.tile_h, tx, h, w, g, level_pool))
+                continue;
             const int x1 = min(w, (tx + 1) * tm.tile_w);
             for (int xb = tx * tm.tile_w; xb < x1; xb += 32) {
                 const int x = xb + lane;
