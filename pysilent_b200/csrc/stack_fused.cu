@@ -610,7 +610,7 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
                                              const f2 *__restrict__ bsum2, const ParamsB &P, const CUtensorMap &tmap,
                                              float *__restrict__ orient, float *__restrict__ line_end,
                                              float *__restrict__ gray, int *__restrict__ winmax, int *__restrict__ tilemax,
-                                             unsigned char *__restrict__ tile_flag)
+                                             unsigned char *__restrict__ tile_flag, const int tm_split)
 {
     using T = TileB<TH, TW, LITE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1112,8 +1112,10 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     }
     if (tilemax && tid >= 32 && tid < 34) {   // [image][tile row][tile column], ordered-int encoding like winmax
         const int lane = tid - 32;
+        // the emit's grid has rows of TH / tm_split: a taller tile (one-wave launches) reports its maximum for each of them
         if (lane == 0 || has_b)
-            tilemax[((size_t)(lane ? img1 : img0) * nby + by) * nbx + bx] = sWin[8 + lane];
+            for (int part = 0; part < tm_split; ++part)
+                tilemax[((size_t)(lane ? img1 : img0) * nby * tm_split + by * tm_split + part) * nbx + bx] = sWin[8 + lane];
     }
     if (issued_line_end) bulk_wait_read();   // the CTA's shared memory must outlive the reads
 }
@@ -1126,7 +1128,7 @@ template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
 __global__ void __launch_bounds__(NT, LITE ? (TH <= 16 ? 5 : 3) : 2)
 stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, const __grid_constant__ CUtensorMap tmap,
                float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
-               int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs)
+               int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs, int tm_split)
 {
     pdl_enter();
     if (!LITE && tile_flag) {
@@ -1138,11 +1140,11 @@ stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, 
             again = true;
             const int bz = t / per_pair, rest = t - bz * per_pair;
             stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, orient, line_end,
-                                                         gray, winmax, tilemax, tile_flag);
+                                                         gray, winmax, tilemax, tile_flag, tm_split);
         }
     } else {
         stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, bsum2, P, tmap,
-                                                     orient, line_end, gray, winmax, tilemax, tile_flag);
+                                                     orient, line_end, gray, winmax, tilemax, tile_flag, tm_split);
     }
 }
 
@@ -1635,8 +1637,9 @@ static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         grid = dim3((unsigned)std::min<long long>((long long)nbx * nby * pairs, 2LL * sms));
     }
+    static_assert(TH % kTileHB == 0, "a launch's tiles are whole multiples of the emit grid's tile rows");
     SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, orient, line_end, gray,
-                                 winmax, tilemax, tile_flag, nbx, nby, pairs));
+                                 winmax, tilemax, tile_flag, nbx, nby, pairs, TH / kTileHB));
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
@@ -1670,6 +1673,8 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
+    if (tiles <= 3LL * sms && (S.b.h % (2 * kTileHB)) == 0)   // ... on tiles twice as tall (half as many CTAs, one wave)
+        return launch_b<2 * kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
     if (!(S.b.quick_thr > 0.0f && tile_flag) || tiles <= 3LL * sms)
         return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
     // quick variant on every tile, then the full variant on the tiles it flagged (none on textured input)
