@@ -1,8 +1,15 @@
 import numpy as np, sys
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
-from oracle import c_oracle
-t = c_oracle.pyramid_tables((1080,1920),(288,192),2**.5)
-L,w = t['L'], t['w']
+import torch
+from pysilent_b200.util.zoom.from_image import PyramidPlan
+# tap tables from the library's own plan (a geometry-only plan needs no GPU)
+plan = PyramidPlan((1080, 1920, 3), torch.uint8, 3, (288, 192), 2 ** .5)
+L, w = plan.levels, plan.w
+t = {'ix': [], 'okx': []}
+for s_ in range(L):
+    iy, wy, ix, wx = plan.level_tables(s_)
+    t['ix'].append(ix)
+    t['okx'].append(ix[:, 0] >= 0)
 FC=3; TW=72; NT=256
 def wavefronts(addrs):  # addrs: f2 indices of up to 32 lanes (None = inactive); LDS.64 -> two half-warps
     tot=0
