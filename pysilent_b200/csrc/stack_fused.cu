@@ -896,7 +896,10 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     }
     if constexpr (LITE) {
         if (__syncthreads_or(task_failed)) {   // nothing of this tile has been written yet
-            if (tid == 0) tile_flag[tile_id] = 1;
+            if (tid == 0) {
+                tile_flag[tile_id] = 1;
+                atomicAdd(reinterpret_cast<int *>(tile_flag - 4), 1);   // the fix-up pass's "anything to do?" counter
+            }
             return;
         }
     } else {
@@ -1132,15 +1135,40 @@ stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, 
 {
     pdl_enter();
     if (!LITE && tile_flag) {
+        // tile_flag[-4 .. -1] counts the tiles the quick pass flagged: on textured input it is 0 and the pass ends here
+        if (*reinterpret_cast<const volatile int *>(tile_flag - 4) == 0) return;
         const int per_pair = nbx * nby, total = per_pair * pairs;
+        __shared__ unsigned s_mask;
         bool again = false;
-        for (int t = blockIdx.x; t < total; t += gridDim.x) {
-            if (!tile_flag[t]) continue;   // (uniform over the CTA)
-            if (again) __syncthreads();   // every thread is done with the previous tile's shared memory
+        // this CTA's tiles are t = blockIdx.x + j * gridDim.x; 32 of them are tested at a time (one per lane of warp 0)
+        for (int j0 = 0; blockIdx.x + (long long)j0 * gridDim.x < total; j0 += 32) {
+            if (again) __syncthreads();   // s_mask of the previous batch has been consumed
+            if (threadIdx.x < 32) {
+                const long long t = blockIdx.x + (long long)(j0 + threadIdx.x) * gridDim.x;
+                bool flagged = false;
+                if (t < total) {
+                    const int bz = (int)(t / per_pair), rest = (int)(t - (long long)bz * per_pair);
+                    // the flags live on the quick pass's grid (tiles of TH / tm_split rows): a taller fix-up tile is redone
+                    // when any of the quick tiles it covers is flagged (the others just get the same bits written again)
+                    for (int part = 0; part < tm_split; ++part)
+                        flagged |= tile_flag[((size_t)bz * nby * tm_split + (rest / nbx) * tm_split + part) * nbx + rest % nbx] != 0;
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, flagged);
+                if (threadIdx.x == 0) s_mask = mask;
+            }
+            __syncthreads();
+            unsigned mask = s_mask;
+            while (mask) {
+                const int bit = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int t = blockIdx.x + (j0 + bit) * gridDim.x;
+                const int bz = t / per_pair, rest = t - bz * per_pair;
+                if (again) __syncthreads();   // every thread is done with the previous tile's shared memory
+                again = true;
+                stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, orient,
+                                                             line_end, gray, winmax, tilemax, tile_flag, tm_split);
+            }
             again = true;
-            const int bz = t / per_pair, rest = t - bz * per_pair;
-            stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, orient, line_end,
-                                                         gray, winmax, tilemax, tile_flag, tm_split);
         }
     } else {
         stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, bsum2, P, tmap,
@@ -1600,7 +1628,7 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
 // ... plus one flag byte per (pair, stack_b tile)
 static size_t stack_flag_bytes(int n, int h, int w)
 {
-    return ((size_t)(n / 2 + 8) * ceil_div(h, kTileHB) * ceil_div(w, 48) + 255) / 256 * 256;
+    return ((size_t)(n / 2 + 8) * ceil_div(h, kTileHB) * ceil_div(w, 48) + 16 + 255) / 256 * 256;
 }
 static size_t stack_plane_bytes(int n, int h, int w) { return ((size_t)(n / 2 + 8) * h * (w + 2) * sizeof(f2) + 255) / 256 * 256; }
 size_t stack_workspace_bytes(int n, int h, int w) { return stack_plane_bytes(n, h, w) + stack_flag_bytes(n, h, w) + 256; }
@@ -1679,9 +1707,11 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
         return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
     // quick variant on every tile, then the full variant on the tiles it flagged (none on textured input)
     const size_t flags = (size_t)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
-    SILENT_CUDA(cudaMemsetAsync(tile_flag, 0, flags, stream));
+    SILENT_CUDA(cudaMemsetAsync(tile_flag - 16, 0, flags + 16, stream));   // flags and the counter in front of them
     rc = launch_b<kTileHB, TW, true, true>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
     if (rc != SILENT_OK) return rc;
+    if ((S.b.h % (2 * kTileHB)) == 0)   // fix-up on tiles twice as tall: a third less halo arithmetic per redone row
+        return launch_b<2 * kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
     return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
 }
 
@@ -1719,7 +1749,7 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     if (geo && winmax) S.b.win = *geo;
     S.a.pair_levels = S.b.pair_levels = levels;
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-    unsigned char *tile_flag = reinterpret_cast<unsigned char *>(bsum2) + stack_plane_bytes(n, h, w);
+    unsigned char *tile_flag = reinterpret_cast<unsigned char *>(bsum2) + stack_plane_bytes(n, h, w) + 16;   // [-4]: counter
     if (pick_tile_w(w) == 48)
         return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream,
                                 between_kernels);
