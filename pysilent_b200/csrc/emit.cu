@@ -298,10 +298,21 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
     // flags below are independent, so they share one memory round trip
     long long sum = 0;
     for (int k = tid; k < n; k += 256) sum += __ldg(level_total + k);
-    // does this level write anything at all?
-    int any = 0;
-    for (int y = tid; y < h; y += 256) any |= __ldg(row_offset + (size_t)n * h + y) & 0x40000000;
-    any = __syncthreads_or(any) && capacity > 0;
+    // the rows of this level that have hits, as a compact list (a warp that walked all rows to find them paid one memory
+    // round trip per row: 24 in a row for a 192-row level)
+    __shared__ int s_hit_y[kEmitMaxRows], s_hit_off[kEmitMaxRows];
+    __shared__ int s_nhit;
+    if (tid == 0) s_nhit = 0;
+    __syncthreads();
+    for (int y = tid; y < h; y += 256) {
+        const int packed = __ldg(row_offset + (size_t)n * h + y);
+        if (packed & 0x40000000) {
+            const int i = atomicAdd(&s_nhit, 1);
+            s_hit_y[i] = y, s_hit_off[i] = packed & 0x3fffffff;
+        }
+    }
+    __syncthreads();
+    const bool any = s_nhit > 0 && capacity > 0;
     if (!any && !last) return;
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_sum[warp] = sum;
@@ -312,12 +323,11 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
     if (!any) return;
     const float *level_pool = pooled + (size_t)n * g.oh * g.ow;
     const int *level_tiles = tm.data + (size_t)n * tm.nty * tm.ntx;
-    for (int y = warp; y < h; y += 8) {   // one warp per row with hits
-        const int packed = __ldg(row_offset + (size_t)n * h + y);
-        if (!(packed & 0x40000000)) continue;
+    for (int i = warp; i < s_nhit; i += 8) {   // one warp per row with hits
+        const int y = s_hit_y[i];
         const float *v = value + ((size_t)n * h + y) * w;
         const float *pool_row = level_pool + nearest_src(y, g.sy, g.oh) * g.ow;
-        long long slot = before + (packed & 0x3fffffff);
+        long long slot = before + s_hit_off[i];
         // the row's tiles are tested by one lane each (their loads overlap), then only flagged tiles are walked in x order
         unsigned flagged = 0;
         for (int t0 = 0; t0 < tm.ntx; t0 += 32) {   // (levels wider than 32 tiles: the walk below re-tests beyond bit 31)
