@@ -145,7 +145,8 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
     const size_t img0 = (size_t)frame0 * plan->levels;
     const int n = nb * plan->levels;
     const unsigned char *frames = (const unsigned char *)frames_dev + frame_bytes(plan) * frame0;
-    int rc = SILENT_OK;
+    int rc = stack_clear_flags(ws.d_stack, n, plan->h, plan->w, s);   // ahead of the kernels: no memset between launches
+    if (rc != SILENT_OK) return rc;
     // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
     // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
     {
@@ -169,7 +170,7 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
                        orient_dev ? orient_dev + img0 * level_elems * 3 : nullptr,
                        line_end_dev ? line_end_dev + img0 * level_elems * 3 : nullptr, ws.d_gray + img0 * level_elems,
                        ws.d_stack, ws.stack_bytes, geo, geo ? ws.d_winmax + img0 * geo->count : nullptr,
-                       ws.d_tilemax + img0 * tm.nty * tm.ntx, s, plan->timing ? plan->ev_mid : nullptr);
+                       ws.d_tilemax + img0 * tm.nty * tm.ntx, s, plan->timing ? plan->ev_mid : nullptr, true);
 }
 
 static int check_pipeline_args(const silent_plan *plan, const silent_stack_weights *W, const void *frames, int batch)

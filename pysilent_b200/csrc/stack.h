@@ -16,7 +16,9 @@ struct WindowGeom {
 size_t stack_workspace_bytes(int n, int h, int w);
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
-                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr);
+                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr,
+                bool flags_clean = false);
+int stack_clear_flags(void *workspace, int n, int h, int w, cudaStream_t stream);
 // tile grid of stack_b_kernel; tilemax is int [n][nty][ntx] (ordered-int maxima of gray per tile, NaN = 0x7fc00000)
 void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx);
 struct TileMaxima {

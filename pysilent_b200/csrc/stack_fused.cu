@@ -1688,7 +1688,7 @@ static int launch_stack_a(const void *pyr, StackPlanHost &S, bool paired_in, int
 
 template <int TW>
 static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int pairs, f2 *bsum2, float *orient,
-                        float *line_end, float *gray, int *winmax, int *tilemax, unsigned char *tile_flag,
+                        float *line_end, float *gray, int *winmax, int *tilemax, unsigned char *tile_flag, bool flags_clean,
                         cudaStream_t stream, cudaEvent_t between_kernels)
 {
     int rc = launch_stack_a<TW>(pyr, S, paired_in, pairs, bsum2, stream);   // (96-wide stack_a tiles: measured 8 % slower)
@@ -1706,8 +1706,10 @@ static int launch_stack(const void *pyr, StackPlanHost &S, bool paired_in, int p
     if (!(S.b.quick_thr > 0.0f && tile_flag) || tiles <= 3LL * sms)
         return launch_b<kTileHB, TW, true, false>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, nullptr, stream);
     // quick variant on every tile, then the full variant on the tiles it flagged (none on textured input)
-    const size_t flags = (size_t)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
-    SILENT_CUDA(cudaMemsetAsync(tile_flag - 16, 0, flags + 16, stream));   // flags and the counter in front of them
+    if (!flags_clean) {   // (the pipeline clears them before the pyramid launch, so that no memset sits between kernels)
+        const size_t flags = (size_t)pairs * ceil_div(S.b.h, kTileHB) * ceil_div(S.b.w, TW);
+        SILENT_CUDA(cudaMemsetAsync(tile_flag - 16, 0, flags + 16, stream));   // flags and the counter in front of them
+    }
     rc = launch_b<kTileHB, TW, true, true>(S, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream);
     if (rc != SILENT_OK) return rc;
     if ((S.b.h % (2 * kTileHB)) == 0)   // fix-up on tiles twice as tall: a third less halo arithmetic per redone row
@@ -1727,9 +1729,18 @@ void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx)
 // pyr: NHWC float32 [n][h][w][3] when pair_levels == 0 (images paired (2p, 2p+1)), else the pair-interleaved planar
 // tensor of pyramid_pair_kernel with `pair_levels` levels per frame (images paired across consecutive frames).
 // winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
+// Zeroes the tile flags (and the counter in front of them) stack_fused will use for n images; the pipeline calls this
+// ahead of the pyramid launch and then passes flags_clean = true.
+int stack_clear_flags(void *workspace, int n, int h, int w, cudaStream_t stream)
+{
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    SILENT_CUDA(cudaMemsetAsync(base + stack_plane_bytes(n, h, w), 0, stack_flag_bytes(n, h, w), stream));
+    return SILENT_OK;
+}
+
 int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const silent_stack_weights *W, float *orient,
                 float *line_end, float *gray, void *workspace, size_t workspace_bytes, const WindowGeom *geo,
-                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels)
+                int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels, bool flags_clean)
 {
     if (!pyr) return fail(SILENT_E_INVAL, "silent_stack_fused: null pyramid");
     if (n <= 0 || h <= 0 || w <= 0) return fail(SILENT_E_INVAL, "silent_stack_fused: bad shape %dx%dx%d", n, h, w);
@@ -1751,10 +1762,10 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     unsigned char *tile_flag = reinterpret_cast<unsigned char *>(bsum2) + stack_plane_bytes(n, h, w) + 16;   // [-4]: counter
     if (pick_tile_w(w) == 48)
-        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream,
-                                between_kernels);
-    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, stream,
-                            between_kernels);
+        return launch_stack<48>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag,
+                                flags_clean, stream, between_kernels);
+    return launch_stack<64>(pyr, S, paired_in, pairs, bsum2, orient, line_end, gray, winmax, tilemax, tile_flag, flags_clean,
+                            stream, between_kernels);
 }
 
 
@@ -1845,7 +1856,7 @@ int silent_stack_fused(const float *pyramid_dev, int n, int h, int w, const sile
                        size_t workspace_bytes, silent_stream stream)
 {
     return silent::stack_fused(pyramid_dev, n, h, w, 0, weights_host, orient_dev, line_end_dev, gray_dev, workspace_dev,
-                               workspace_bytes, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+                               workspace_bytes, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr, false);
 }
 
 }  // extern "C"
