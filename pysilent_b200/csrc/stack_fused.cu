@@ -31,6 +31,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <mutex>
+#include <vector>
 
 #include "plan.h"
 #include "stack.h"
@@ -233,14 +235,36 @@ __device__ __forceinline__ void pair_images(int p, int levels, int n, int &a, in
     if (!has_b) b = a;
 }
 
+// Shared-memory bank groups (16 bytes, 8 per 128-byte line) of S1's accesses: task (row triple rt, channel c, run k) reads
+// x at (3 rt + i) * X_PITCH + c * X_PLANE + 8 k (+ 2 q) float2 and writes a at the same expression with the A constants.
+// With odd pitches (in 16-byte units) and PLANE strides == 1 (mod 8 units) both map a task to the group
+// (s * rt + c + 4 k) mod 8 (s = 3 * pitch units, odd), so ONE deal of tasks to lanes (s1_deal, built on the host) makes
+// the eight lanes of almost every quarter-warp hit eight different groups for loads and stores alike. The x planes get
+// there with one extra (unused) row in the TMA box, the a planes with 14 float2 of padding.
+constexpr int plane_rows_for_unit_stride(int rows, int pitch)
+{
+    for (int extra = 0; extra < 8; ++extra)
+        if (((rows + extra) * (pitch / 2)) % 8 == 1) return rows + extra;
+    return rows;
+}
+constexpr int plane_size_for_unit_stride(int size)
+{
+    for (int extra = 0; extra < 16; extra += 2)
+        if (((size + extra) / 2) % 8 == 1) return size + extra;
+    return size;
+}
+
 template <int TH, int TW>
 struct TileA {
-    static constexpr int X_ROWS = TH + 4, A_ROWS = TH + 2;      // x: halo 2 (origin -2), a: halo 1 (origin -1)
+    static constexpr int A_ROWS = TH + 2;                       // a: halo 1 (origin -1)
     static constexpr int A_RUNS = (TW + 2 + kPX - 1) / kPX;     // S1 runs start at column -1
     static constexpr int B_RUNS = TW / kPX;
     static constexpr int X_PITCH = round_pitch(kPX * (A_RUNS - 1) + 10 > TW + 4 ? kPX * (A_RUNS - 1) + 10 : TW + 4);
     static constexpr int A_PITCH = round_pitch(kPX * A_RUNS > kPX * (B_RUNS - 1) + 10 ? kPX * A_RUNS : kPX * (B_RUNS - 1) + 10);
-    static constexpr int X_PLANE = X_ROWS * X_PITCH, A_PLANE = A_ROWS * A_PITCH;
+    static constexpr int X_ROWS = plane_rows_for_unit_stride(TH + 4, X_PITCH);   // x: halo 2 (origin -2) + bank padding rows
+    static constexpr int X_PLANE = X_ROWS * X_PITCH, A_PLANE = plane_size_for_unit_stride(A_ROWS * A_PITCH);
+    static constexpr bool kDealOk = (X_PLANE / 2) % 8 == 1 && (A_PLANE / 2) % 8 == 1 && ((3 * X_PITCH / 2) % 8) == ((3 * A_PITCH / 2) % 8);
+    static constexpr int kBankStep = (3 * X_PITCH / 2) % 8;    // bank groups per row triple (odd)
     static constexpr int O_PITCH = round_pitch(TW);   // staged output rows (overlaid on the x planes)
     static_assert(TH * O_PITCH <= 3 * X_PLANE, "output staging must fit in the x planes");
     static constexpr size_t kSmemBytes = (size_t)(3 * X_PLANE + 3 * A_PLANE) * sizeof(f2);
@@ -263,7 +287,8 @@ __host__ __device__ constexpr bool rgby_nonzero(int tap, int ci, int co)
 // 24 + 8 FFMA2/FADD2 instead of 53. Part of the canonical FUSED order (oracle/silent_oracle.c: so_rgby_shared).
 template <int TH, int TW, int NT, bool S1_DEPTHWISE, int S2_MODE, bool PAIRED_IN>
 __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ input, const __grid_constant__ ParamsA P,
-                                                     const __grid_constant__ CUtensorMap tmap, f2 *__restrict__ bsum2)
+                                                     const __grid_constant__ CUtensorMap tmap, f2 *__restrict__ bsum2,
+                                                     const unsigned char *__restrict__ s1_deal)
 {
     using T = TileA<TH, TW>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -375,9 +400,14 @@ __global__ void __launch_bounds__(NT) stack_a_kernel(const void *__restrict__ in
         // the canonical (ky, kx) order.
         static_assert(T::A_ROWS % 3 == 0, "S1 row triples");
         constexpr int TRIPLES = T::A_ROWS / 3;
-        for (int t = tid; t < 3 * TRIPLES * T::A_RUNS; t += NT) {
-            const int rt = t % TRIPLES, rest = t / TRIPLES;
-            const int c = rest % 3, k = rest / 3;   // lanes walk the row triples first: conflict-free when TRIPLES % 8 == 0
+        static_assert(3 * TRIPLES * T::A_RUNS <= NT || !T::kDealOk, "the dealt form of S1 is one task per thread");
+        for (int t = tid; t < (s1_deal ? NT : 3 * TRIPLES * T::A_RUNS); t += NT) {   // (dealt: any lane may hold a task)
+            int rt = t % TRIPLES, c = (t / TRIPLES) % 3, k = t / (3 * TRIPLES);
+            if (s1_deal) {   // bank-conflict-free deal of the tasks to the lanes (see TileA)
+                const int packed = __ldg(s1_deal + tid);
+                if (packed == 255) break;
+                rt = packed & 7, c = (packed >> 3) & 3, k = packed >> 5;
+            }
             const int r0 = 3 * rt, gx0 = tx0 - 1 + kPX * k;
             f2 wt[9];
 #pragma unroll
@@ -1611,6 +1641,63 @@ struct ThreadsB {
     static constexpr int value = (TileB<TH, TW, LITE>::CS_ROWS * TileB<TH, TW, LITE>::C_RUNS + 31) / 32 * 32;
 };
 
+// S1's deal of tasks (row triple, channel, run) to the lanes of stack_a (see TileA): octets of tasks whose bank groups
+// (step * rt + c + 4 k) mod 8 are all different, as many full ones as the class sizes allow; the left-over tasks fill the
+// remaining octets so that no group repeats more than it must. One table per tile shape and device, built on first use.
+template <int TW>
+static const unsigned char *s1_deal_table()
+{
+    using T = TileA<kTileHA, TW>;
+    constexpr int NT = ThreadsA<TW>::value, TRIPLES = T::A_ROWS / 3, TASKS = 3 * TRIPLES * T::A_RUNS;
+    if (!T::kDealOk || TASKS > NT || TRIPLES > 8 || T::A_RUNS > 8) return nullptr;
+    static std::mutex lock;
+    static unsigned char *tables[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> guard(lock);
+    if (tables[dev]) return tables[dev];
+    std::vector<int> by_unit[8];
+    for (int k = 0; k < T::A_RUNS; ++k)
+        for (int c = 0; c < 3; ++c)
+            for (int rt = 0; rt < TRIPLES; ++rt) by_unit[(T::kBankStep * rt + c + 4 * k) % 8].push_back(rt | (c << 3) | (k << 5));
+    std::vector<unsigned char> deal(NT, 255);
+    const int octets = NT / 8;
+    std::vector<int> used(octets * 8, 0);   // [octet][unit]: tasks of that unit already in the octet
+    int next = 0;
+    // pass 1: full octets (one task of every unit) while every class still has a task; pass 2: the rest, each task into the
+    // octet where its unit is rarest (lanes of an octet are consecutive, so an octet is a quarter-warp of 128-bit accesses)
+    std::vector<int> fill(octets, 0);
+    for (; next < octets; ++next) {
+        bool all = true;
+        for (int u = 0; u < 8; ++u) all = all && !by_unit[u].empty();
+        if (!all) break;
+        for (int u = 0; u < 8; ++u) {
+            deal[next * 8 + fill[next]++] = (unsigned char)by_unit[u].back();
+            by_unit[u].pop_back();
+            used[next * 8 + u] = 1;
+        }
+    }
+    for (int u = 0; u < 8; ++u)
+        while (!by_unit[u].empty()) {
+            int best = -1;
+            for (int o = next; o < octets; ++o)
+                if (fill[o] < 8 && (best < 0 || used[o * 8 + u] < used[best * 8 + u] ||
+                                    (used[o * 8 + u] == used[best * 8 + u] && fill[o] < fill[best])))
+                    best = o;
+            if (best < 0) return nullptr;   // cannot happen: TASKS <= NT
+            deal[best * 8 + fill[best]++] = (unsigned char)by_unit[u].back();
+            by_unit[u].pop_back();
+            ++used[best * 8 + u];
+        }
+    unsigned char *d = nullptr;
+    if (cudaMalloc(&d, NT) != cudaSuccess || cudaMemcpy(d, deal.data(), NT, cudaMemcpyHostToDevice) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    tables[dev] = d;
+    return d;
+}
+
 template <int TW, bool DW, int RGBY, bool PAIRED>
 static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, f2 *bsum2, int pairs, cudaStream_t stream)
 {
@@ -1619,7 +1706,8 @@ static int launch_a(const void *pyr, const ParamsA &P, const CUtensorMap &tmap, 
     auto kern = stack_a_kernel<kTileHA, TW, kThreadsA, DW, RGBY, PAIRED>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
     const dim3 grid(ceil_div(P.w, TW), ceil_div(P.h, kTileHA), pairs);
-    SILENT_CUDA(launch_dependent(kern, grid, dim3(kThreadsA), T::kSmemBytes, stream, pyr, P, tmap, bsum2));
+    const unsigned char *deal = DW ? s1_deal_table<TW>() : nullptr;
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(kThreadsA), T::kSmemBytes, stream, pyr, P, tmap, bsum2, deal));
     SILENT_LAUNCH_CHECK("stack_a_kernel");
     return SILENT_OK;
 }
