@@ -172,6 +172,8 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     const uint8_t *frameA = P.frames + (size_t)(2 * q) * frame_bytes;
     const uint8_t *frameB = (2 * q + 1 < P.B) ? frameA + frame_bytes : frameA;
 
+    // the tile's word span is requested first: its latency overlaps the table staging below instead of following the barrier
+    const int2 span = __ldg(reinterpret_cast<const int2 *>(P.words + ((size_t)level * kPairMaxTiles + bx) * 2));
     for (int i = tid; i < th * kTaps; i += kPairThreads) {
         const int oy = oy0 + i / kTaps;
         const bool ok = oy < h && __ldg(idx_y + (size_t)oy * kTaps) >= 0;
@@ -182,8 +184,7 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
 
     // ---- the coarsest level is the first reader of a frame pair (finer levels then hit L2): ask L2 for the same tile of
     //      the NEXT pair now, one bulk prefetch per (tap row, frame), so that CTA finds its rows in L2 instead of HBM --
-    const int wlo_pf = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2);
-    const int nw_pf = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2 + 1);
+    const int wlo_pf = span.x, nw_pf = span.y;
     if (level == P.L - 1 && 2 * (q + 1) < P.B && nw_pf > 0) {
         for (int i = tid; i < 2 * th * kTaps; i += kPairThreads) {
             const int e = i >> 1, f = 2 * (q + 1) + (i & 1);
@@ -197,8 +198,7 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
 
     // ---- phase V: column sums over the 6 y-taps, 16 byte-columns (one aligned 128-bit load per tap row and frame) per
     //      task: 12 independent 16-byte loads in flight per thread cover the HBM/L2 latency ---------------------------
-    const int wlo = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2);   // multiples of 4 words
-    const int nw = __ldg(P.words + ((size_t)level * kPairMaxTiles + bx) * 2 + 1);
+    const int wlo = span.x, nw = span.y;   // first 32-bit word of a frame row (a multiple of 4) and word count
     const int nq = nw >> 2;
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
     for (int t = tid; t < th * nq; t += kPairThreads) {
