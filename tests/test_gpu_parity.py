@@ -811,3 +811,23 @@ def test_orientation_bank_shape_sweep_bit_exact(c_oracle):
         res = pipe.run_frames(torch.from_numpy(frames).cuda())
         assert tuple(res.orient.shape) == pyr.shape[:3] + (8,)
         _check_stack(res, ref, None, "bank %s" % (shape,))
+
+
+def test_fused_stack_early_out_threshold_sweep(c_oracle, default_filters):
+    """The regulator's early-out (quad sums prove blur > 1) around its own threshold: noise pyramids scaled so that the
+    7x7 blur of the stripe sum sweeps from far below 1 (every gain != 1) through ~1 (mixed) to far above (every gain = 1).
+    Bitwise against the oracle for every scale -- an unsound early-out would hand out a gain of exactly 1 where the
+    reference's min(blur, 1) is below 1."""
+    from pysilent_b200 import LineEndPipeline, _ops
+    weights = LineEndPipeline().stack_weights()
+    base = np.random.RandomState(77).rand(2, 40, 56, 3).astype(np.float32)
+    mixed = 0
+    for scale in (1e-5, 3e-5, 6e-5, 1e-4, 1.5e-4, 2e-4, 3e-4, 4e-4, 6e-4, 1e-3, 3e-3, 1e-2, 1.0, 30.0):
+        x = (base * np.float32(scale * 255)).astype(np.float32)
+        orient, line_end, gray = _ops.stack_fused(x, weights)
+        ref = c_oracle.line_end_stack(x, default_filters)
+        assert_bits(orient, ref["orient"], "orient, scale %g" % scale)
+        assert_bits(line_end, ref["padded"], "padded_line_end, scale %g" % scale)
+        gain_one = np.isclose(ref["orient"], ref["stripe"], rtol=0, atol=0) | (ref["stripe"] == 0)
+        mixed += 0 < gain_one.mean() < 1
+    assert mixed >= 3, "the sweep must cross the regime where only part of the gains are 1"
