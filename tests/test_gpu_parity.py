@@ -831,3 +831,19 @@ def test_fused_stack_early_out_threshold_sweep(c_oracle, default_filters):
         gain_one = np.isclose(ref["orient"], ref["stripe"], rtol=0, atol=0) | (ref["stripe"] == 0)
         mixed += 0 < gain_one.mean() < 1
     assert mixed >= 3, "the sweep must cross the regime where only part of the gains are 1"
+
+
+def test_pipeline_low_contrast_frames(c_oracle, default_filters):
+    """uint8 frames with only a few grey levels: the blur of the stripe sum sits around 1, so the quick stack_b pass flags
+    some tiles and not others and the fix-up pass redoes exactly those. Device and host entry points, bitwise."""
+    from pysilent_b200 import LineEndPipeline
+    pipe = LineEndPipeline(zoom_ratio=1.3)
+    for levels_of_grey in (2, 3, 5, 9, 20):
+        rs = np.random.RandomState(500 + levels_of_grey)
+        frames = rs.randint(0, levels_of_grey, size=(3, 480, 640, 3)).astype(np.uint8)
+        frames[1, 100:300, 200:500] = 1           # a flat patch inside the low-contrast noise
+        pyr, ref = _oracle_pipeline(c_oracle, frames, (288, 192), 1.3, default_filters)
+        res = pipe.run_frames(torch.from_numpy(frames).cuda())
+        _check_stack(res, ref, None, "low contrast, %d grey levels" % levels_of_grey)
+    host = pipe.run_host(frames)
+    _check_stack(host, ref, None, "low contrast, host")
