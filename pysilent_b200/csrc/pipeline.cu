@@ -80,6 +80,7 @@ silent_plan::~silent_plan()
     if (d_tables) cudaFree(d_tables);
     if (d_pair_words) cudaFree(d_pair_words);
     if (d_pair_htab) cudaFree(d_pair_htab);
+    if (d_pair_ytab) cudaFree(d_pair_ytab);
 }
 
 extern "C" {

@@ -175,7 +175,8 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
     }
     if (const char *e = std::getenv("SILENT_PAIR_TILEW")) kPairTileW = std::max(8, std::min(kPairTileWMax, std::atoi(e)));   // tuning knob
     plan->pair_tile_w = kPairTileW;
-    plan->pair_ok = L > 0 && L <= kPairMaxLevels && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3;
+    plan->pair_ok = L > 0 && L <= kPairMaxLevels && ceil_div(w, kPairTileW) <= kPairMaxTiles && p->frame_c >= 3 &&
+                    (int64_t)p->frame_h * p->frame_w * p->frame_c < INT32_MAX;   // row offsets inside a frame are 32-bit
     for (int s = 0; s < L && plan->pair_ok; ++s) {
         PairLevel &pl = plan->pair[s];
         pl.ntx = ceil_div(w, kPairTileW);
@@ -237,29 +238,37 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 return fail(SILENT_E_CUDA, "upload of tap tables failed: %s", cudaGetErrorString(e));
             }
             if (plan->pair_ok) {   // per-level / per-tile word spans of the frame-pair pyramid kernel
-                std::vector<int> words((size_t)L * kPairMaxTiles * 2, 0);
+                // (word_lo, nwords, M, 0): M = 2^32 / groups + 1 turns the kernel's task -> (row, group) division into one
+                // multiply-high (exact for task < 2^32 / groups; groups = 1 is special-cased there)
+                std::vector<int> words((size_t)L * kPairMaxTiles * 4, 0);
                 for (int s = 0; s < L; ++s)
                     for (int t = 0; t < plan->pair[s].ntx; ++t) {
-                        words[((size_t)s * kPairMaxTiles + t) * 2] = plan->pair[s].word_lo[t];
-                        words[((size_t)s * kPairMaxTiles + t) * 2 + 1] = plan->pair[s].nwords[t];
+                        int *e4 = &words[((size_t)s * kPairMaxTiles + t) * 4];
+                        e4[0] = plan->pair[s].word_lo[t];
+                        e4[1] = plan->pair[s].nwords[t];
+                        const uint32_t groups = (uint32_t)plan->pair[s].nwords[t] / 4;
+                        const uint32_t magic = groups > 1 ? (uint32_t)((1ull << 32) / groups + 1) : 0u;
+                        std::memcpy(&e4[2], &magic, 4);
                     }
                 e = cudaMalloc(&plan->d_pair_words, words.size() * sizeof(int));
                 if (e == cudaSuccess)
                     e = cudaMemcpy(plan->d_pair_words, words.data(), words.size() * sizeof(int), cudaMemcpyHostToDevice);
-                // phase-H table: per (level, output column, channel) the six positions of its taps in a padded column-sum
-                // row -- up to the tile's own origin, which is a constant the kernel subtracts -- and the six weights
-                // (zero for columns the reference leaves undefined). position(B) = B + 2 * (B >> 4) for the absolute byte
-                // column B = tap * frame_c + channel; tiles start at multiples of 16 bytes, so the shift distributes.
+                // phase-H table: per (level, output column, channel) the six offsets of its taps in the padded column-sum
+                // row of ITS tile and the six weights (offset 0 / weight 0 for columns the reference leaves undefined).
+                // position(B) = B + 2 * (B >> 4) for the absolute byte column B = tap * frame_c + channel; tiles start at
+                // multiples of 16 bytes, so the shift distributes and the tile origin is 4 * word_lo + 2 * (word_lo >> 2).
                 std::vector<int32_t> htab((size_t)L * w * 3 * 12, 0);
                 for (int s = 0; s < L; ++s)
                     for (int ox = 0; ox < w; ++ox) {
                         const int32_t *tx = &plan->idx_x[((size_t)s * w + ox) * kTaps];
                         const float *gx = &plan->w_x[((size_t)s * w + ox) * kTaps];
+                        const int wlo = plan->pair[s].word_lo[ox / kPairTileW];
+                        const int origin = 4 * wlo + (kPairVGroup - 16) * (wlo >> 2);
                         for (int c = 0; c < 3; ++c) {
                             int32_t *row = &htab[(((size_t)s * w + ox) * 3 + c) * 12];
                             for (int i = 0; i < kTaps; ++i) {
                                 const int B = tx[0] >= 0 ? tx[i] * p->frame_c + c : -1;
-                                row[i] = B >= 0 ? B + (kPairVGroup - 16) * (B >> 4) : -1;
+                                row[i] = B >= 0 ? B + (kPairVGroup - 16) * (B >> 4) - origin : 0;
                                 const float wv = tx[0] >= 0 ? gx[i] : 0.0f;
                                 std::memcpy(&row[6 + i], &wv, 4);
                             }
@@ -268,6 +277,24 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_htab, htab.size() * sizeof(int32_t));
                 if (e == cudaSuccess)
                     e = cudaMemcpy(plan->d_pair_htab, htab.data(), htab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+                // phase-V table: per (level, output row) the byte offsets of its six tap rows inside a frame and the six
+                // weights, three 128-bit loads per task (a row the reference leaves undefined has offset[0] = -1)
+                std::vector<int32_t> ytab((size_t)L * h * 12, 0);
+                const int64_t row_bytes = (int64_t)p->frame_w * p->frame_c;
+                for (int s = 0; s < L; ++s)
+                    for (int oy = 0; oy < h; ++oy) {
+                        const int32_t *ty = &plan->idx_y[((size_t)s * h + oy) * kTaps];
+                        const float *gy = &plan->w_y[((size_t)s * h + oy) * kTaps];
+                        int32_t *row = &ytab[((size_t)s * h + oy) * 12];
+                        for (int j = 0; j < kTaps; ++j) {
+                            row[j] = ty[0] >= 0 ? (int32_t)(ty[j] * row_bytes) : -1;
+                            const float wv = ty[0] >= 0 ? gy[j] : 0.0f;
+                            std::memcpy(&row[6 + j], &wv, 4);
+                        }
+                    }
+                if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_ytab, ytab.size() * sizeof(int32_t));
+                if (e == cudaSuccess)
+                    e = cudaMemcpy(plan->d_pair_ytab, ytab.data(), ytab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
                 if (e != cudaSuccess) {
                     delete plan;
                     return fail(SILENT_E_CUDA, "upload of pyramid tile spans failed: %s", cudaGetErrorString(e));

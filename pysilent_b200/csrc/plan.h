@@ -68,8 +68,9 @@ struct silent_plan {
     std::vector<silent::PairLevel> pair;   // per level
     bool pair_ok = false;
     int pair_tile_w = 64;                  // output columns per tile of the frame-pair pyramid kernel (see plan.cu)
-    int *d_pair_words = nullptr;           // [L][kPairMaxTiles][2]: (word_lo, nwords) per level and x tile
-    int32_t *d_pair_htab = nullptr;        // [L][w][3][12]: phase-H tap positions (6 ints) and weights (6 floats), see plan.cu
+    int *d_pair_words = nullptr;           // [L][kPairMaxTiles][4]: (word_lo, nwords, 2^32 / groups + 1, 0) per level and x tile
+    int32_t *d_pair_htab = nullptr;        // [L][w][3][12]: phase-H tap offsets in the tile's column-sum row (6 ints) and weights (6 floats)
+    int32_t *d_pair_ytab = nullptr;        // [L][h][12]: phase-V byte offsets of the six tap rows in a frame ([0] < 0: zero row) and weights
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;

@@ -132,17 +132,17 @@ constexpr int kVGroup = kPairVGroup;   // float2 slots per group of 16 byte-colu
 struct PairParams {
     const uint8_t *frames;
     f2 *xpair;
-    const int32_t *idx_y, *idx_x;   // tap tables of all levels: [L][h][6], [L][w][6]
-    const float *w_y, *w_x;
-    const int *words;               // [L][kPairMaxTiles][2]: first 32-bit word of a frame row and word count per x tile
-    const int32_t *htab;            // [L][w][3][12]: phase-H tap positions and weights (plan.cu)
-    int H, row_bytes, FC;           // frame rows, bytes per frame row, interleaved channels
-    int h, w, L, B, ntx, tile_w;
-    // ONE launch covers every level: blockIdx.x enumerates the tiles of a frame pair with the COARSEST level first (it
-    // pulls the whole frame through L2; the finer levels, whose crops are subsets, then hit L2), blockIdx.y the pair.
-    int th[kPairMaxLevels];           // output rows per tile
-    int vpitch[kPairMaxLevels];       // float2 per row of the column-sum buffer
-    int tile_start[kPairMaxLevels + 1];   // by order position k (level = L - 1 - k)
+    const int4 *ytab;     // [L][h][3]: phase-V byte offsets of the six tap rows inside a frame + six weights (plan.cu)
+    const int4 *words;    // [L][kPairMaxTiles]: (first 32-bit word of a frame row, word count, 2^32 / groups + 1, 0) per x tile
+    const int4 *htab;     // [L][w][3][3]: phase-H tap offsets in the tile's column-sum row + six weights (plan.cu)
+    size_t frame_bytes;
+    int h, w, L, B, tile_w;
+    // ONE launch covers every level: blockIdx.x is the x tile, blockIdx.y enumerates the tile rows of a frame pair with
+    // the COARSEST level first (it pulls the whole frame through L2; the finer levels, whose crops are subsets, then hit
+    // L2), blockIdx.z the pair.
+    int th[kPairMaxLevels];            // output rows per tile
+    int vpitch[kPairMaxLevels];        // float2 per row of the column-sum buffer
+    int row_start[kPairMaxLevels + 1];   // first blockIdx.y by order position k (level = L - 1 - k)
 };
 
 // byte k of `word` as an exact float: PRMT builds the bit pattern of 2^23 + byte, the caller subtracts 2^23 (FADD2)
@@ -159,68 +159,59 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
 
     const int tid = threadIdx.x;
     int k = 0;
-    while (k + 1 < P.L && (int)blockIdx.x >= P.tile_start[k + 1]) ++k;
-    const int level = P.L - 1 - k, local = blockIdx.x - P.tile_start[k];
-    const int bx = local % P.ntx, by = local / P.ntx, q = blockIdx.y;
+    while (k + 1 < P.L && (int)blockIdx.y >= P.row_start[k + 1]) ++k;
+    const int level = P.L - 1 - k, bx = blockIdx.x, by = blockIdx.y - P.row_start[k], q = blockIdx.z;
     const int th = P.th[level], vpitch = P.vpitch[level], h = P.h, w = P.w;
-    const int32_t *idx_y = P.idx_y + (size_t)level * h * kTaps;
-    const float *w_y = P.w_y + (size_t)level * h * kTaps;
     const int oy0 = by * th;
-    int *sTy = reinterpret_cast<int *>(sV + (size_t)th * vpitch);   // [th][6] source rows (-1: row is zero)
-    float *sWy = reinterpret_cast<float *>(sTy + th * kTaps);       // [th][6]
-    const size_t frame_bytes = (size_t)P.H * P.row_bytes;
-    const uint8_t *frameA = P.frames + (size_t)(2 * q) * frame_bytes;
-    const uint8_t *frameB = (2 * q + 1 < P.B) ? frameA + frame_bytes : frameA;
-
-    // the tile's word span is requested first: its latency overlaps the table staging below instead of following the barrier
-    const int2 span = __ldg(reinterpret_cast<const int2 *>(P.words + ((size_t)level * kPairMaxTiles + bx) * 2));
-    for (int i = tid; i < th * kTaps; i += kPairThreads) {
-        const int oy = oy0 + i / kTaps;
-        const bool ok = oy < h && __ldg(idx_y + (size_t)oy * kTaps) >= 0;
-        sTy[i] = ok ? __ldg(idx_y + (size_t)oy * kTaps + i % kTaps) : -1;
-        sWy[i] = ok ? __ldg(w_y + (size_t)oy * kTaps + i % kTaps) : 0.0f;
-    }
-    __syncthreads();
+    const int rows = min(th, h - oy0);
+    // (first word, word count, reciprocal of the group count) of this x tile; nothing is staged in shared memory before
+    // phase V: every task reads its row's tap offsets and weights straight from the (L1-resident) table
+    const int4 span = __ldg(P.words + (size_t)level * kPairMaxTiles + bx);
+    const int4 *ytab = P.ytab + ((size_t)level * h + oy0) * 3;
+    const uint8_t *frameA = P.frames + (size_t)(2 * q) * P.frame_bytes + (size_t)span.x * 4;
+    const uint8_t *frameB = (2 * q + 1 < P.B) ? frameA + P.frame_bytes : frameA;
+    const int nq = span.y >> 2;
+    const uint32_t magic = (uint32_t)span.z;
 
     // ---- the coarsest level is the first reader of a frame pair (finer levels then hit L2): ask L2 for the same tile of
     //      the NEXT pair now, one bulk prefetch per (tap row, frame), so that CTA finds its rows in L2 instead of HBM --
-    const int wlo_pf = span.x, nw_pf = span.y;
-    if (level == P.L - 1 && 2 * (q + 1) < P.B && nw_pf > 0) {
-        for (int i = tid; i < 2 * th * kTaps; i += kPairThreads) {
-            const int e = i >> 1, f = 2 * (q + 1) + (i & 1);
-            const int row = sTy[e];
-            if (row >= 0 && f < P.B) {
-                const uint8_t *src = P.frames + (size_t)f * frame_bytes + (size_t)row * P.row_bytes + (size_t)wlo_pf * 4;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nw_pf * 4) : "memory");
+    if (level == P.L - 1 && 2 * (q + 1) < P.B && nq > 0) {
+        const int32_t *yoff = reinterpret_cast<const int32_t *>(ytab);
+        for (int i = tid; i < 2 * rows * kTaps; i += kPairThreads) {
+            const int e = i >> 1, f = 2 + (i & 1), r = e / kTaps;
+            const int off = __ldg(yoff + 12 * r + (e - kTaps * r));
+            if (__ldg(yoff + 12 * r) >= 0 && 2 * q + f < P.B) {
+                const uint8_t *src = frameA + (size_t)f * P.frame_bytes + off;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(span.y * 4) : "memory");
             }
         }
     }
 
     // ---- phase V: column sums over the 6 y-taps, 16 byte-columns (one aligned 128-bit load per tap row and frame) per
     //      task: 12 independent 16-byte loads in flight per thread cover the HBM/L2 latency ---------------------------
-    const int wlo = span.x, nw = span.y;   // first 32-bit word of a frame row (a multiple of 4) and word count
-    const int nq = nw >> 2;
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
-    for (int t = tid; t < th * nq; t += kPairThreads) {
-        const int r = t / nq, qi = t - r * nq;
+    for (int t = tid; t < rows * nq; t += kPairThreads) {
+        const int r = nq > 1 ? (int)__umulhi((uint32_t)t, magic) : t, qi = t - r * nq;
+        const int4 y0 = __ldg(ytab + 3 * r), y1 = __ldg(ytab + 3 * r + 1), y2 = __ldg(ytab + 3 * r + 2);
         f2 acc[16];
-        if (sTy[r * kTaps] < 0) {
+        if (y0.x < 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
         } else {
+            const int yoff[kTaps] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y};
+            const float wyv[kTaps] = {__int_as_float(y1.z), __int_as_float(y1.w), __int_as_float(y2.x),
+                                      __int_as_float(y2.y), __int_as_float(y2.z), __int_as_float(y2.w)};
             uint4 qa[kTaps], qb[kTaps];
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
-                const size_t off = (size_t)sTy[r * kTaps + j] * P.row_bytes;
-                qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + off) + (wlo >> 2) + qi);
-                qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + off) + (wlo >> 2) + qi);
+                qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + yoff[j]) + qi);
+                qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + yoff[j]) + qi);
             }
             // The first tap is a plain product: fma(w, v, +0) and w * v differ only when the product is -0 (a negative
             // weight on a zero byte), and a -0 column sum cannot change any output bit (phase H adds every term to +0).
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
-                const float wy = sWy[r * kTaps + j];
-                const f2 wy2 = make_float2(wy, wy);
+                const f2 wy2 = make_float2(wyv[j], wyv[j]);
                 const uint32_t wa[4] = {qa[j].x, qa[j].y, qa[j].z, qa[j].w}, wb[4] = {qb[j].x, qb[j].y, qb[j].z, qb[j].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -237,41 +228,33 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
 #pragma unroll
         for (int k = 0; k < 8; ++k) dst[k] = make_float4(acc[2 * k].x, acc[2 * k].y, acc[2 * k + 1].x, acc[2 * k + 1].y);
     }
-    __syncthreads();
+    if (nq == 0 && tid < rows) sV[(size_t)tid * vpitch] = make_float2(0.0f, 0.0f);   // a tile without any defined column:
+    __syncthreads();                                                                  // phase H reads slot 0 with weight 0
 
     // ---- phase H: chain over the 6 x-taps. A thread owns one (output column, channel) and walks all rows of the tile:
-    //      its six column-sum offsets and weights are set up once, each row then costs 6 LDS.64 + 6 FFMA2 + 1 store.
-    //      (192 of the 256 threads work here.)
+    //      its six column-sum offsets and weights come from a host-built table (three 128-bit loads, no arithmetic), each
+    //      row then costs 6 LDS.64 + 6 FFMA2 + 1 store.
     // Lanes interleave (column, channel): three consecutive lanes read three consecutive column sums (the B, G, R bytes
     // of one source pixel), so a warp's gather touches a third of the 128-byte lines it would with one channel per warp.
     const size_t plane = (size_t)h * w;
-    const int rows = min(th, h - oy0);
     for (int item = tid; item < 3 * P.tile_w; item += kPairThreads) {   // one pass when the CTA has >= 3 * tile_w threads
         const int c = item % 3;
         const int ox = bx * P.tile_w + item / 3;
         if (ox >= w) break;
-        // six tap positions + six weights of this (column, channel): three 128-bit loads of a table that already holds the
-        // padded positions up to the tile origin (the per-tap index arithmetic and twelve scalar loads it replaces were
-        // 12 % of the kernel's instructions with 3-row tiles)
-        const int4 *tab = reinterpret_cast<const int4 *>(P.htab + ((((size_t)level * w + ox) * 3 + c) * 12));
+        const int4 *tab = P.htab + ((size_t)level * w + ox) * 9 + 3 * c;
         const int4 t0 = __ldg(tab), t1 = __ldg(tab + 1), t2 = __ldg(tab + 2);
-        const int pos[kTaps] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y};
+        const int off[kTaps] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y};
         const float wv[kTaps] = {__int_as_float(t1.z), __int_as_float(t1.w), __int_as_float(t2.x),
                                  __int_as_float(t2.y), __int_as_float(t2.z), __int_as_float(t2.w)};
-        const int origin = 4 * wlo + (kVGroup - 16) * (wlo >> 2);
-        int off[kTaps];
         f2 wx[kTaps];
 #pragma unroll
-        for (int i = 0; i < kTaps; ++i) {
-            off[i] = pos[0] >= 0 ? pos[i] - origin : 0;
-            wx[i] = make_float2(wv[i], wv[i]);
-        }
+        for (int i = 0; i < kTaps; ++i) wx[i] = make_float2(wv[i], wv[i]);
         f2 *out = P.xpair + (((size_t)q * P.L + level) * 3 + c) * plane + (size_t)oy0 * w + ox;
         for (int r = 0; r < rows; ++r) {
             const f2 *row = sV + (size_t)r * vpitch;
             f2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[off[i]], acc);   // zero weights when !col_ok
+            for (int i = 0; i < kTaps; ++i) acc = __ffma2_rn(wx[i], row[off[i]], acc);   // zero weights for undefined columns
             out[(size_t)r * w] = acc;
         }
     }
@@ -303,28 +286,27 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     PairParams P;
     P.frames = (const uint8_t *)frames_dev;
     P.xpair = (f2 *)xpair_dev;
-    P.idx_y = plan->d_idx_y, P.w_y = plan->d_w_y, P.idx_x = plan->d_idx_x, P.w_x = plan->d_w_x;
-    P.words = plan->d_pair_words;
-    P.htab = plan->d_pair_htab;
-    P.H = p.frame_h;
-    P.row_bytes = p.frame_w * p.frame_c;
-    P.FC = p.frame_c;
+    P.ytab = reinterpret_cast<const int4 *>(plan->d_pair_ytab);
+    P.words = reinterpret_cast<const int4 *>(plan->d_pair_words);
+    P.htab = reinterpret_cast<const int4 *>(plan->d_pair_htab);
+    P.frame_bytes = (size_t)p.frame_h * p.frame_w * p.frame_c;
     P.h = plan->h, P.w = plan->w, P.L = plan->levels, P.B = batch;
-    P.ntx = plan->pair[0].ntx;
     P.tile_w = plan->pair_tile_w;
     size_t smem = 0;
-    int tiles = 0;
+    int tile_rows = 0;
     for (int k = 0; k < plan->levels; ++k) {   // coarsest level first
         const int s = plan->levels - 1 - k;
         const PairLevel &pl = plan->pair[s];
         P.th[s] = pl.th;
         P.vpitch[s] = pl.vpitch;
-        P.tile_start[k] = tiles;
-        tiles += pl.ntx * ceil_div(plan->h, pl.th);
-        smem = std::max(smem, (size_t)pl.th * pl.vpitch * sizeof(f2) + (size_t)pl.th * kTaps * 8);
+        P.row_start[k] = tile_rows;
+        tile_rows += ceil_div(plan->h, pl.th);
+        smem = std::max(smem, std::max((size_t)16, (size_t)pl.th * pl.vpitch * sizeof(f2)));
     }
-    P.tile_start[plan->levels] = tiles;
-    SILENT_CUDA(launch_dependent(pyramid_pair_kernel, dim3(tiles, pairs), dim3(kPairThreads), smem, stream, P));
+    P.row_start[plan->levels] = tile_rows;
+    if (tile_rows > 65535) return fail(SILENT_E_SHAPE, "too many tile rows for one launch (%d)", tile_rows);
+    SILENT_CUDA(launch_dependent(pyramid_pair_kernel, dim3(plan->pair[0].ntx, tile_rows, pairs), dim3(kPairThreads), smem,
+                                 stream, P));
     SILENT_LAUNCH_CHECK("pyramid_pair_kernel");
     return SILENT_OK;
 }
