@@ -187,6 +187,19 @@ enum {
 int silent_pointwise(const float *x_dev, const float *y_dev, size_t count, int kind, float *out_dev,
                      silent_stream stream);
 
+/* Everything LineEndDisplayer.compile builds after gray_line_end_tensor (recognition_testing.py:79-100) in two launches:
+ * centroids_disp_dev [n,h,w,1] = 255 - get_centroids(gray / 255)[0] * 255, centroids2_disp_dev [n,half_h,half_w,1] = the
+ * same on resize_nearest(gray, (half_h, half_w)), and from importance = clip(total_pool * (255 / 4), 1, 256) - 1 the
+ * boosting pair of get_boosting(for_visualizing=True): fired_disp_dev [n,oh,ow,3] = has_fired * importance * 255 and
+ * update_disp_dev [n,oh,ow,3] = energy * normer + centerer (normer = 255 / (exhaustion_max + excitation_max), centerer =
+ * excitation_max / (exhaustion_max + excitation_max) * 255, boosting.py:37-39); energy_dev [n,oh,ow,1] is updated in place
+ * as by silent_get_boosting. oh = ceil(h / region_h), ow = ceil(w / region_w); scratch_dev: 2 * n * oh * ow floats.
+ * Bit-identical to the chain silent_pointwise / silent_get_centroids / silent_resize_nearest / silent_get_boosting. */
+int silent_display_tensors(const float *gray_dev, int n, int h, int w, int region_h, int region_w, int half_h, int half_w,
+                           float *energy_dev, float exhaustion_max, float excitation_max, int recovery_mode, float normer,
+                           float centerer, float *centroids_disp_dev, float *centroids2_disp_dev, float *fired_disp_dev,
+                           float *update_disp_dev, float *scratch_dev, silent_stream stream);
+
 /* ---- multi-GPU: the path's only exchange is the feature-point gather ------------------------------------- */
 
 /* Packs one rank's points for a single fixed-size all-gather: packed_dev [capacity + 1][4] int64 = the first

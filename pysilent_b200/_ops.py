@@ -209,6 +209,33 @@ def pointwise(x, kind, y=None):
     return out
 
 
+def display_tensors(gray, energy, region_h, region_w, half_h, half_w, exhaustion_max, excitation_max, recovery_mode):
+    """The display chain after ``gray_line_end_tensor`` in two launches (``silent_display_tensors``): returns
+    ``(255 - centroids * 255, 255 - centroids2 * 255, fired * importance * 255 [.., 3], energy display [.., 3])`` and
+    updates ``energy`` in place."""
+    g = as_device_tensor(gray)
+    n, h, w, c = _nhwc(g, "display_tensors")
+    oh, ow = -(-h // region_h), -(-w // region_w)
+    if c != 1 or tuple(energy.shape) != (n, oh, ow, 1) or not energy.is_cuda or energy.dtype != torch.float32 \
+            or not energy.is_contiguous():
+        raise ValueError("display_tensors needs a one-channel gray tensor and a contiguous CUDA float32 energy tensor "
+                         "[n, ceil(h / region_h), ceil(w / region_w), 1]")
+    dev = g.device
+    cent = torch.empty((n, h, w, 1), dtype=torch.float32, device=dev)
+    cent2 = torch.empty((n, int(half_h), int(half_w), 1), dtype=torch.float32, device=dev)
+    fired = torch.empty((n, oh, ow, 3), dtype=torch.float32, device=dev)
+    update = torch.empty((n, oh, ow, 3), dtype=torch.float32, device=dev)
+    scratch = torch.empty((2 * n * oh * ow,), dtype=torch.float32, device=dev)
+    normer = 255.0 / (exhaustion_max + excitation_max)                                   # boosting.py:37-38
+    centerer = (excitation_max / (exhaustion_max + excitation_max)) * 255.0
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().silent_display_tensors(
+            ptr(g), n, h, w, int(region_h), int(region_w), int(half_h), int(half_w), ptr(energy), float(exhaustion_max),
+            float(excitation_max), int(recovery_mode), float(normer), float(centerer), ptr(cent), ptr(cent2), ptr(fired),
+            ptr(update), ptr(scratch), stream_ptr()), "silent_display_tensors")
+    return cent, cent2, fired, update
+
+
 def stack_fused(pyramid, weights, want_orient=True, want_line_end=True, want_gray=True):
     x = as_device_tensor(pyramid)
     n, h, w, c = _nhwc(x, "stack_fused")

@@ -15,9 +15,10 @@ import torch
 
 from . import _lib, _ops
 from .pipeline import LineEndPipeline
-from .util.centroids import get_centroids
+from .util.centroids import get_centroids, _region as region_dims
 from .util.color import get_value_from_color
 from .util.energy.boosting import get_boosting, initialize_boosting
+from .util.energy.recovery import recovery_mode
 
 debug = True
 
@@ -46,15 +47,26 @@ class LineEndDisplayer(LineEndPipeline):
         self._pinned = {}
 
     # -- the part of compile() after gray_line_end_tensor (recognition_testing.py:79-100) -------------------------------
-    def display_tensors(self, orient, padded_line_end, gray=None):
-        """Device tensors in the order ``run()`` fetches them; updates ``energy_values``."""
+    def display_tensors(self, orient, padded_line_end, gray=None, fused=True):
+        """Device tensors in the order ``run()`` fetches them; updates ``energy_values``. ``fused`` (default) runs the
+        chain as the two launches of ``silent_display_tensors``; ``fused=False`` composes the stand-alone operators one by
+        one, as the reference graph is written (same bits, seventeen launches)."""
         if gray is None:
             gray = get_value_from_color(padded_line_end)                                          # :77
         shape = tuple(orient.shape)
+        half = (np.asarray(shape[1:3], dtype=np.float32) / np.float32(m.e ** .5)).astype(np.int32)   # :82
+        if fused:
+            rh, rw = region_dims(self.centroid_region_shape)
+            state_shape = (shape[0], -(-shape[1] // rh), -(-shape[2] // rw), 1)
+            if self.pyramid_tensor_shape != shape or self.energy_values is None:                  # pre_compile, :45-57
+                self.pyramid_tensor_shape = shape
+                self.energy_values = torch.full(state_shape, 8.0, dtype=torch.float32, device=gray.device)
+            cent, cent2, fired, update = _ops.display_tensors(gray, self.energy_values, rh, rw, int(half[0]), int(half[1]),
+                                                              1, 1, recovery_mode(False, True))   # :79-87
+            return [orient, cent, cent2, fired, update, padded_line_end]                          # :98-100
         centroids, importances = get_centroids(_ops.pointwise(gray, _lib.PW_DIV255), self.centroid_region_shape,
                                                debug=True)                                        # :79-80
         importances = _ops.pointwise(importances, _lib.PW_IMPORTANCE)                             # :81
-        half = (np.asarray(shape[1:3], dtype=np.float32) / np.float32(m.e ** .5)).astype(np.int32)   # :82
         im2 = _ops.resize_nearest(gray, int(half[0]), int(half[1]))                               # :83
         centroids2, _ = get_centroids(_ops.pointwise(im2, _lib.PW_DIV255), self.centroid_region_shape, debug=True)
         if self.pyramid_tensor_shape != shape or self.energy_values is None:                      # pre_compile, :45-57

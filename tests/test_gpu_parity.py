@@ -609,6 +609,33 @@ def test_displayer_matches_reference_goldens(goldens, c_oracle):
             assert_close(iso.energy_values, D["%s_step%d_energy" % (name, step)], "energy vs reference code")
 
 
+@pytest.mark.parametrize("h,w,region", [(192, 288, 3), (100, 149, 3), (37, 53, 4), (64, 96, 2)])
+def test_display_tensors_fused_matches_operator_chain(h, w, region):
+    """``silent_display_tensors`` (two launches) against the chain of stand-alone operators the reference graph is written
+    as (recognition_testing.py:79-100), bitwise, over three frames of boosting state -- on level shapes the region does not
+    divide (ragged last blocks, pixel -> block through the float nearest-neighbour scale) and with empty blocks (0 / 0)."""
+    from pysilent_b200 import LineEndDisplayer
+    rs = np.random.RandomState(h * 7 + w)
+    n = 3
+    a, b = LineEndDisplayer(), LineEndDisplayer()
+    a.centroid_region_shape = b.centroid_region_shape = [1, region, region]
+    for step in range(3):
+        gray = rs.uniform(0, 255, size=(n, h, w, 1)).astype(np.float32)
+        gray[rs.uniform(size=gray.shape) < 0.4] = 0.0
+        gray[0, : 3 * region, : 5 * region] = 0.0               # empty blocks: centroid 0 / 0 = NaN, importance 0
+        gray[1] = 0.0 if step == 1 else gray[1]
+        g = torch.from_numpy(gray).cuda()
+        orient = torch.zeros((n, h, w, 3), device="cuda")
+        padded = torch.zeros((n, h, w, 3), device="cuda")
+        fused = a.display_tensors(orient, padded, g, fused=True)
+        chain = b.display_tensors(orient, padded, g, fused=False)
+        for i in (1, 2, 3, 4):
+            assert tuple(fused[i].shape) == tuple(chain[i].shape), (i, fused[i].shape, chain[i].shape)
+            assert_bits(fused[i], chain[i].cpu().numpy(), "step %d display tensor %d" % (step, i))
+        assert_bits(a.energy_values, b.energy_values.cpu().numpy(), "boosting state after step %d" % step)
+    assert np.isnan(fused[1].cpu().numpy()).any()
+
+
 def test_displayer_callback_structure_and_state(c_oracle, default_filters):
     """callback(frame, cam_id) returns ``[frame] + 6 lists of per-level images`` (recognition_testing.py:144); the
     boosting state persists across frames and is reset when the frame shape changes; display() scales by 1/255."""
