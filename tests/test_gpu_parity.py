@@ -283,6 +283,21 @@ def test_pipeline_baseline_configs_bit_exact(config, shape, scale, batch, c_orac
     assert len(cb[1]) == pyr.shape[0] // batch and np.array_equal(cb[1][0], ref["orient"][0], equal_nan=True)
 
 
+@pytest.mark.parametrize("shape,scale", [((2000, 112), 1.5), ((240, 1920), 2 ** .5), ((96, 1600), 1.7)])
+def test_pipeline_extreme_aspect_frames_bit_exact(shape, scale, c_oracle, default_filters):
+    """Frames far from the level aspect ratio: the coarse crops leave the frame on one axis, so whole x tiles of the
+    pyramid kernel have no defined column (tile without a word span) and hundreds of output rows are undefined (zero
+    rows). Device and host entry points bitwise against the oracle, odd batch."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(7, i, *shape) for i in range(3)])
+    pipe = LineEndPipeline(zoom_ratio=scale)
+    pyr, ref = _oracle_pipeline(c_oracle, frames, (288, 192), scale, default_filters)
+    assert (pyr == 0).all(axis=(2, 3)).any() or (pyr == 0).all(axis=(1, 3)).any()   # undefined rows or columns exist
+    res = pipe.run_frames(torch.from_numpy(frames).cuda())
+    _check_stack(res, ref, None, "extreme aspect %s device" % (shape,))
+    _check_stack(pipe.run_host(frames), ref, None, "extreme aspect %s host" % (shape,))
+
+
 def test_pipeline_structured_frames_nan_and_gain_paths(c_oracle, default_filters):
     from oracle import silent_oracle as lit
     from pysilent_b200 import LineEndPipeline
