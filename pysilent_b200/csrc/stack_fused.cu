@@ -105,6 +105,22 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
                  : "memory");
 }
+// ---- TMA tile stores: ONE cp.async.bulk.tensor moves a whole staged tile (kTileStoreRows rows of one image) shared ->
+//      global. The output tensor is described as [image][row][tile column][floats of one tile row] and the box is FOUR
+//      floats wider than a tile row: the box then reads the staging buffer at its padded row pitch (an odd multiple of
+//      16 bytes, what keeps the staging writes conflict-free) and the hardware clips the extra floats, like the rows of a
+//      ragged last tile, as out of bounds. (A first version with 16-byte chunks as the inner dimension was 20 % SLOWER
+//      than one bulk copy per row: the TMA unit works row by row of the inner dimension.)
+struct StoreMaps {
+    CUtensorMap orient, line_end, gray;
+};
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap *map, const void *ssrc, int tile_x, int y, int img)
+{
+    if (SILENT_ABLATE & 1) return;
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(ssrc)), "r"(0), "r"(tile_x), "r"(y), "r"(img)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -199,6 +215,22 @@ __device__ __forceinline__ bool bulk_rows(const float *__restrict__ stage, int s
     }
     if (leader) bulk_commit();
     return leader;
+}
+
+// the staged rows of a tile ([2][TH][pitch] floats: image A's rows, then image B's) as TMA tile stores of kTileStoreRows rows
+constexpr int kTileStoreRows = 16;
+template <int TH>
+__device__ __forceinline__ void tile_store_images(const CUtensorMap *map, const float *stage, int pitch, int bx, int ty0, int h,
+                                                  int img0, int img1, bool has_b)
+{
+    static_assert(TH % kTileStoreRows == 0, "tiles are whole multiples of the store box");
+#pragma unroll
+    for (int part = 0; part < TH / kTileStoreRows; ++part) {
+        const int y = ty0 + part * kTileStoreRows;
+        if (y >= h) break;
+        tma_store_tile(map, stage + (size_t)part * kTileStoreRows * pitch, bx, y, img0);
+        if (has_b) tma_store_tile(map, stage + (size_t)(TH + part * kTileStoreRows) * pitch, bx, y, img1);
+    }
 }
 
 __device__ __forceinline__ void store_cols8(f2 *__restrict__ dst, const f2 (&v)[kPX])
@@ -586,6 +618,7 @@ struct ParamsB {
     int h, w, n;
     int pair_levels;  // see pair_images()
     int use_tma;      // load the channel-sum tile with one TMA box copy
+    int tma_store;    // outputs leave as TMA tile stores (StoreMaps valid) instead of one bulk copy per staged row
     int prefetch_pairs, pairs;   // quick variant: L2 prefetch distance in image pairs (0: off), number of pairs
     WindowGeom win;   // fused region maxima (stack.h)
 };
@@ -638,7 +671,7 @@ struct TileB {
 template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
 __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const int bz, const int nbx, const int nby,
                                              const f2 *__restrict__ bsum2, const ParamsB &P, const CUtensorMap &tmap,
-                                             float *__restrict__ orient, float *__restrict__ line_end,
+                                             const StoreMaps &M, float *__restrict__ orient, float *__restrict__ line_end,
                                              float *__restrict__ gray, int *__restrict__ winmax, int *__restrict__ tilemax,
                                              unsigned char *__restrict__ tile_flag, const int tm_split)
 {
@@ -941,6 +974,10 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     //      the three phases) they do all of this on their own, synchronised by a named barrier, while the S5 warps start
     //      the end filter at once; the copy drains while S5 computes ---------------------------------------------
     const bool bulk_ok = (w % 4) == 0;   // staged rows start and end on 16-byte boundaries of the global tensors
+    // TMA tile stores need 128-byte aligned shared-memory sources: every 16-row part of the staging buffers must be one
+    constexpr bool kStageTileStore = (kTileStoreRows * T::ST_PITCH * 4) % 128 == 0;
+    constexpr bool kGrayTileStore = ((size_t)T::FRONT_F2 * sizeof(f2)) % 128 == 0 && (kTileStoreRows * T::G_PITCH * 4) % 128 == 0;
+    const bool tile_store = kStageTileStore && P.tma_store != 0;   // (the host checked w % TW == 0 and built the maps)
     constexpr int kS5Warps = (TH * T::E_RUNS + 31) / 32, kIdleWarps = NT / 32 - kS5Warps;
     constexpr bool kSideRestage = kIdleWarps >= 1;   // (16-row tiles: 3 warps run S5, the 4th restages and stores orient)
     constexpr int kRestageFirst = kSideRestage ? 32 * kS5Warps : 0, kRestageThreads = kSideRestage ? 32 * kIdleWarps : NT;
@@ -965,7 +1002,13 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
         } else {
             __syncthreads();
         }
-        if (bulk_ok) {
+        if (tile_store) {
+            if (tid == kRestageFirst) {   // two tile stores per 16 rows (one per image) instead of a bulk copy per row
+                tile_store_images<TH>(&M.orient, sStage, T::ST_PITCH, bx, ty0, h, img0, img1, has_b);
+                bulk_commit();
+                issued_orient = true;
+            }
+        } else if (bulk_ok) {
             issued_orient = bulk_rows<TH>(sStage, T::ST_PITCH, orient, img0, img1, has_b, ty0, h, (size_t)w * 3, (size_t)tx0 * 3,
                                           (uint32_t)(min(TW, w - tx0) * 3), warp_u, kRestageFirst / 32, kRestageThreads / 32,
                                           leader);
@@ -1125,11 +1168,23 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     // ---- copy-out: staged rows -> global NHWC, one bulk store per row ---------------------------------------------------
     fence_async_smem();
     __syncthreads();
-    if (gray && bulk_ok)   // 2 * TH rows of TW floats, dealt like the line_end rows
+    if (gray && tile_store && kGrayTileStore) {
+        if (tid == 32) {
+            tile_store_images<TH>(&M.gray, sGray, T::G_PITCH, bx, ty0, h, img0, img1, has_b);
+            bulk_commit();
+            issued_line_end = true;
+        }
+    } else if (gray && bulk_ok)   // 2 * TH rows of TW floats, dealt like the line_end rows
         issued_line_end |= bulk_rows<TH>(sGray, T::G_PITCH, gray, img0, img1, has_b, ty0, h, (size_t)w, (size_t)tx0,
                                          (uint32_t)min(TW, w - tx0), warp_u, 0, NT / 32, leader);
     if (line_end) {
-        if (bulk_ok) {
+        if (tile_store) {
+            if (tid == 0) {
+                tile_store_images<TH>(&M.line_end, sStage, T::ST_PITCH, bx, ty0, h, img0, img1, has_b);
+                bulk_commit();
+                issued_line_end = true;
+            }
+        } else if (bulk_ok) {
             issued_line_end |= bulk_rows<TH>(sStage, T::ST_PITCH, line_end, img0, img1, has_b, ty0, h, (size_t)w * 3,
                                              (size_t)tx0 * 3, (uint32_t)(min(TW, w - tx0) * 3), warp_u, 0, NT / 32, leader);
         } else {
@@ -1160,7 +1215,7 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
 template <int TH, int TW, int NT, bool SYM3, bool OWNOTH, bool LITE>
 __global__ void __launch_bounds__(NT, LITE ? (TH <= 16 ? 5 : 3) : 2)
 stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, const __grid_constant__ CUtensorMap tmap,
-               float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
+               const __grid_constant__ StoreMaps M, float *__restrict__ orient, float *__restrict__ line_end, float *__restrict__ gray, int *__restrict__ winmax,
                int *__restrict__ tilemax, unsigned char *__restrict__ tile_flag, int nbx, int nby, int pairs, int tm_split)
 {
     pdl_enter();
@@ -1195,14 +1250,14 @@ stack_b_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsB P, 
                 const int bz = t / per_pair, rest = t - bz * per_pair;
                 if (again) __syncthreads();   // every thread is done with the previous tile's shared memory
                 again = true;
-                stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, orient,
+                stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(rest % nbx, rest / nbx, bz, nbx, nby, bsum2, P, tmap, M, orient,
                                                              line_end, gray, winmax, tilemax, tile_flag, tm_split);
             }
             again = true;
         }
     } else {
         stack_b_tile<TH, TW, NT, SYM3, OWNOTH, LITE>(blockIdx.x, blockIdx.y, blockIdx.z, gridDim.x, gridDim.y, bsum2, P, tmap,
-                                                     orient, line_end, gray, winmax, tilemax, tile_flag, tm_split);
+                                                     M, orient, line_end, gray, winmax, tilemax, tile_flag, tm_split);
     }
 }
 
@@ -1524,6 +1579,33 @@ static bool make_pair_map(CUtensorMap *map, const void *base, int w, int rows, l
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// Store view of an NHWC float32 output [n][h][w][ch] for TMA tile stores (see tma_store_tile): dims (floats of a tile row,
+// tiles per row, rows, images), box (tile row + pad, 1, box_rows, 1). False if the geometry does not allow it.
+static bool make_tile_store_map(CUtensorMap *map, const void *base, int n, int h, int w, int ch, int tw, int pad, int box_rows)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        encode = (EncodeTiledFn)fn;
+    }
+    const int tile_floats = tw * ch;
+    if (!base || ((uintptr_t)base & 15) != 0 || w % tw != 0 || tile_floats % 4 != 0 || (tile_floats + pad) % 4 != 0 ||
+        tile_floats + pad > 256 || box_rows > 256)
+        return false;
+    const cuuint64_t row_bytes = (cuuint64_t)w * ch * 4;
+    const cuuint64_t dims[4] = {(cuuint64_t)tile_floats, (cuuint64_t)(w / tw), (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)tile_floats * 4, row_bytes, row_bytes * h};
+    const cuuint32_t box[4] = {(cuuint32_t)(tile_floats + pad), 1, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static f2 dup(float v) { return make_float2(v, v); }
 
 struct StackPlanHost {
@@ -1743,6 +1825,13 @@ static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float
     auto kern = stack_b_kernel<TH, TW, NT, STRUCTURED, STRUCTURED, LITE>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TB::kSmemBytes));
     S.b.use_tma = (w % 2) == 0 && make_pair_map(&map_b, bsum2, w + 2, h, pairs, TB::B_PITCH, TB::B_ROWS, 1);
+    // outputs as TMA tile stores (one per 16 rows and image instead of one bulk copy per row) when every tile is whole in x
+    StoreMaps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    S.b.tma_store = (!orient || make_tile_store_map(&maps.orient, orient, S.b.n, h, w, 3, TW, TB::ST_PITCH - 3 * TW, kTileStoreRows)) &&
+                    (!line_end || make_tile_store_map(&maps.line_end, line_end, S.b.n, h, w, 3, TW, TB::ST_PITCH - 3 * TW, kTileStoreRows)) &&
+                    (!gray || make_tile_store_map(&maps.gray, gray, S.b.n, h, w, 1, TW, TB::G_PITCH - TW, kTileStoreRows));
+    if (const char *e = std::getenv("SILENT_B_TILE_STORE")) S.b.tma_store = S.b.tma_store && std::atoi(e) != 0;   // tuning knob
     S.b.pairs = pairs;
     S.b.prefetch_pairs = 4;   // measured: 2 / 4 / 8 alike (-5 % on the quick pass), 0 = off
     if (const char *e = std::getenv("SILENT_B_PREFETCH")) S.b.prefetch_pairs = std::atoi(e);   // tuning knob
@@ -1754,8 +1843,8 @@ static int launch_b(StackPlanHost &S, int pairs, f2 *bsum2, float *orient, float
         grid = dim3((unsigned)std::min<long long>((long long)nbx * nby * pairs, 2LL * sms));
     }
     static_assert(TH % kTileHB == 0, "a launch's tiles are whole multiples of the emit grid's tile rows");
-    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, orient, line_end, gray,
-                                 winmax, tilemax, tile_flag, nbx, nby, pairs, TH / kTileHB));
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), TB::kSmemBytes, stream, (const f2 *)bsum2, S.b, map_b, maps, orient, line_end,
+                                 gray, winmax, tilemax, tile_flag, nbx, nby, pairs, TH / kTileHB));
     SILENT_LAUNCH_CHECK("stack_b_kernel");
     return SILENT_OK;
 }
