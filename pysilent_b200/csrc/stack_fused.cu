@@ -1282,6 +1282,7 @@ struct ParamsBank {
     f2 w5[9][kNB];   // end, depthwise [tap][orientation]
     float reg_value, reg_root, clip_max, quick_thr;
     int border, h, w, n, pair_levels;
+    int tma_store;   // orient / line_end leave as TMA tile stores (StoreMaps valid)
 };
 
 template <int TH, int TW>
@@ -1313,7 +1314,7 @@ __device__ __forceinline__ void store_cols4(f2 *__restrict__ dst, const f2 (&v)[
 
 template <int TH, int TW, int NT>
 __global__ void __launch_bounds__(NT, 2) stack_bank_kernel(const f2 *__restrict__ bsum2, const __grid_constant__ ParamsBank P,
-                                                           float *__restrict__ orient, float *__restrict__ line_end,
+                                                           const __grid_constant__ StoreMaps M, float *__restrict__ orient, float *__restrict__ line_end,
                                                            float *__restrict__ gray)
 {
     using T = TileBank<TH, TW>;
@@ -1435,6 +1436,8 @@ __global__ void __launch_bounds__(NT, 2) stack_bank_kernel(const f2 *__restrict_
 
     // ---- orient = d: centre rows of the planes, restaged NHWC (4 orientations = one 128-bit chunk per pixel and image) --
     const bool bulk_ok = (w % 4) == 0;
+    constexpr bool kStageTileStore = (kTileStoreRows * T::ST_PITCH * 4) % 128 == 0;
+    const bool tile_store = kStageTileStore && P.tma_store != 0;
     bool issued = false;
     if (orient) {
         for (int t = tid; t < TH * T::E_RUNS; t += NT) {
@@ -1455,7 +1458,13 @@ __global__ void __launch_bounds__(NT, 2) stack_bank_kernel(const f2 *__restrict_
         }
         fence_async_smem();
         __syncthreads();
-        if (bulk_ok) {
+        if (tile_store) {
+            if (tid == 0) {
+                tile_store_images<TH>(&M.orient, sStage, T::ST_PITCH, blockIdx.x, ty0, h, img0, img1, has_b);
+                bulk_commit();
+                issued = true;
+            }
+        } else if (bulk_ok) {
             issued = bulk_rows<TH>(sStage, T::ST_PITCH, orient, img0, img1, has_b, ty0, h, (size_t)w * kNB, (size_t)tx0 * kNB,
                                    (uint32_t)(min(TW, w - tx0) * kNB), warp_u, 0, NT / 32, leader);
         } else {
@@ -1532,7 +1541,13 @@ __global__ void __launch_bounds__(NT, 2) stack_bank_kernel(const f2 *__restrict_
     __syncthreads();
     issued = false;
     if (line_end) {
-        if (bulk_ok) {
+        if (tile_store) {
+            if (tid == 0) {
+                tile_store_images<TH>(&M.line_end, sStage, T::ST_PITCH, blockIdx.x, ty0, h, img0, img1, has_b);
+                bulk_commit();
+                issued = true;
+            }
+        } else if (bulk_ok) {
             issued = bulk_rows<TH>(sStage, T::ST_PITCH, line_end, img0, img1, has_b, ty0, h, (size_t)w * kNB, (size_t)tx0 * kNB,
                                    (uint32_t)(min(TW, w - tx0) * kNB), warp_u, 0, NT / 32, leader);
         } else {
@@ -1581,7 +1596,8 @@ static bool make_pair_map(CUtensorMap *map, const void *base, int w, int rows, l
 }
 // Store view of an NHWC float32 output [n][h][w][ch] for TMA tile stores (see tma_store_tile): dims (floats of a tile row,
 // tiles per row, rows, images), box (tile row + pad, 1, box_rows, 1). False if the geometry does not allow it.
-static bool make_tile_store_map(CUtensorMap *map, const void *base, int n, int h, int w, int ch, int tw, int pad, int box_rows)
+static bool make_tile_store_map(CUtensorMap *map, const void *base, int n, int h, int w, int ch, int tw, int pad, int box_rows,
+                                int elem_floats = 1)   // 2: 8-byte elements (tile rows of more than 252 floats: boxes hold <= 256 elements)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -1595,14 +1611,14 @@ static bool make_tile_store_map(CUtensorMap *map, const void *base, int n, int h
     }
     const int tile_floats = tw * ch;
     if (!base || ((uintptr_t)base & 15) != 0 || w % tw != 0 || tile_floats % 4 != 0 || (tile_floats + pad) % 4 != 0 ||
-        tile_floats + pad > 256 || box_rows > 256)
+        (tile_floats + pad) / elem_floats > 256 || box_rows > 256)
         return false;
     const cuuint64_t row_bytes = (cuuint64_t)w * ch * 4;
-    const cuuint64_t dims[4] = {(cuuint64_t)tile_floats, (cuuint64_t)(w / tw), (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t dims[4] = {(cuuint64_t)(tile_floats / elem_floats), (cuuint64_t)(w / tw), (cuuint64_t)h, (cuuint64_t)n};
     const cuuint64_t strides[3] = {(cuuint64_t)tile_floats * 4, row_bytes, row_bytes * h};
-    const cuuint32_t box[4] = {(cuuint32_t)(tile_floats + pad), 1, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)((tile_floats + pad) / elem_floats), 1, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr,
+    return encode(map, elem_floats == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -2014,7 +2030,12 @@ int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const si
     auto kern = stack_bank_kernel<kBankTH, kBankTW, NT>;
     SILENT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::kSmemBytes));
     const dim3 grid(ceil_div(w, kBankTW), ceil_div(h, kBankTH), pairs);
-    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), T::kSmemBytes, stream, (const f2 *)bsum2, B, orient, line_end, gray));
+    StoreMaps maps;   // tile rows are 256 floats: described in 8-byte elements (a box holds at most 256 of them)
+    std::memset(&maps, 0, sizeof(maps));
+    B.tma_store = (!orient || make_tile_store_map(&maps.orient, orient, n, h, w, kNB, kBankTW, T::ST_PITCH - kNB * kBankTW, kTileStoreRows, 2)) &&
+                  (!line_end || make_tile_store_map(&maps.line_end, line_end, n, h, w, kNB, kBankTW, T::ST_PITCH - kNB * kBankTW, kTileStoreRows, 2));
+    if (const char *e = std::getenv("SILENT_B_TILE_STORE")) B.tma_store = B.tma_store && std::atoi(e) != 0;   // tuning knob
+    SILENT_CUDA(launch_dependent(kern, grid, dim3(NT), T::kSmemBytes, stream, (const f2 *)bsum2, B, maps, orient, line_end, gray));
     SILENT_LAUNCH_CHECK("stack_bank_kernel");
     return SILENT_OK;
 }
