@@ -250,7 +250,7 @@ struct ParamsA {
     f2 s2s[9];        // S2 mode 2: the shared surround kernel S (centre tap unused)
     f2 s2c[6];        // S2 mode 2: centre taps d0, d1, d2 (ci -> ci), e12 (1 -> 2), e21 (2 -> 1), and the constant 2
     int h, w, n;      // level shape, number of images
-    int pair_levels;  // image pairing: pair p holds images (a, a + pair_levels), see pair_images()
+    unsigned long long pair_levels;  // image pairing: pair p holds images (a, a + levels), packed by pack_pair_levels()
     int use_tma;      // PAIRED_IN only: load the tile with one TMA box copy
     int prefetch_pairs;   // L2 prefetch distance in image pairs (0: off)
 };
@@ -258,9 +258,18 @@ struct ParamsA {
 // Which two images ride in the float2 lanes of pair p. With pair_levels = 1 these are images (2p, 2p + 1); the
 // pipeline pairs the SAME level of two consecutive frames (pair_levels = levels per frame), which lets the pyramid
 // kernel share its tap tables between the lanes. Lane B mirrors lane A (and is never stored) when it has no image.
-__device__ __forceinline__ void pair_images(int p, int levels, int n, int &a, int &b, bool &has_b)
+// levels is packed with its reciprocal: pair_levels = levels | (2^32 / levels + 1) << 32 (pack_pair_levels), exact for
+// p < 2^32 / levels -- one multiply-high instead of a 20-instruction integer division in every thread
+__host__ __device__ inline unsigned long long pack_pair_levels(int levels)
 {
-    const int frame_pair = p / levels, s = p - frame_pair * levels;
+    const unsigned long long magic = levels > 1 ? (1ull << 32) / (unsigned)levels + 1 : 0ull;
+    return (unsigned)levels | (magic << 32);
+}
+__device__ __forceinline__ void pair_images(int p, unsigned long long packed, int n, int &a, int &b, bool &has_b)
+{
+    const int levels = (int)(unsigned)packed;
+    const unsigned magic = (unsigned)(packed >> 32);
+    const int frame_pair = levels > 1 ? (int)__umulhi((unsigned)p, magic) : p, s = p - frame_pair * levels;
     a = frame_pair * 2 * levels + s;
     b = a + levels;
     has_b = b < n;
@@ -616,7 +625,7 @@ struct ParamsB {
     float quick_thr;  // S4 early-out: a channel sum >= quick_thr under ANY blur tap proves m >= 1 (0: early-out disabled)
     int border;
     int h, w, n;
-    int pair_levels;  // see pair_images()
+    unsigned long long pair_levels;  // see pair_images() / pack_pair_levels()
     int use_tma;      // load the channel-sum tile with one TMA box copy
     int tma_store;    // outputs leave as TMA tile stores (StoreMaps valid) instead of one bulk copy per staged row
     int prefetch_pairs, pairs;   // quick variant: L2 prefetch distance in image pairs (0: off), number of pairs
@@ -1194,8 +1203,9 @@ __device__ __forceinline__ void stack_b_tile(const int bx, const int by, const i
     if (P.win.count) {
         if (tid < 8) {
             const int lane = tid >> 2, win = tid & 3;
-            if (win < P.win.count && (lane == 0 || has_b) && sWin[tid] != 0)
-                atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], sWin[tid]);
+            const int v = sWin[tid];
+            if (win < P.win.count && (lane == 0 || has_b) && v != 0)
+                atomicMax(&winmax[(size_t)(lane ? img1 : img0) * P.win.count + win], v);
         }
     }
     if (tilemax && tid >= 32 && tid < 34) {   // [image][tile row][tile column], ordered-int encoding like winmax
@@ -1281,7 +1291,8 @@ struct ParamsBank {
     f2 wb[49];       // blur
     f2 w5[9][kNB];   // end, depthwise [tap][orientation]
     float reg_value, reg_root, clip_max, quick_thr;
-    int border, h, w, n, pair_levels;
+    int border, h, w, n;
+    unsigned long long pair_levels;   // pack_pair_levels()
     int tma_store;   // orient / line_end leave as TMA tile stores (StoreMaps valid)
 };
 
@@ -1951,7 +1962,7 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
     int rc = pack_stack_params(W, n, h, w, &S);
     if (rc != SILENT_OK) return rc;
     if (geo && winmax) S.b.win = *geo;
-    S.a.pair_levels = S.b.pair_levels = levels;
+    S.a.pair_levels = S.b.pair_levels = pack_pair_levels(levels);
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     unsigned char *tile_flag = reinterpret_cast<unsigned char *>(bsum2) + stack_plane_bytes(n, h, w) + 16;   // [-4]: counter
     if (pick_tile_w(w) == 48)
@@ -2007,7 +2018,7 @@ int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const si
         if ((double)blur_min * (double)T >= 1.0001 && T < 1.0e20f) B.quick_thr = T;
     }
     B.reg_value = W->regulation_value, B.reg_root = W->regulation_root, B.clip_max = W->clip_max, B.border = W->border;
-    B.h = h, B.w = w, B.n = n, B.pair_levels = pair_levels;
+    B.h = h, B.w = w, B.n = n, B.pair_levels = pack_pair_levels(pair_levels);
 
     // S1 + S2 -> channel sum, exactly as in the three-orientation pipeline
     silent_stack_weights tmp;
@@ -2019,7 +2030,7 @@ int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const si
     StackPlanHost S;
     int rc = pack_stack_params(&tmp, n, h, w, &S);
     if (rc != SILENT_OK) return rc;
-    S.a.pair_levels = pair_levels;
+    S.a.pair_levels = pack_pair_levels(pair_levels);
     f2 *bsum2 = reinterpret_cast<f2 *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     rc = pick_tile_w(w) == 48 ? launch_stack_a<48>(xpair, S, true, pairs, bsum2, stream)
                               : launch_stack_a<64>(xpair, S, true, pairs, bsum2, stream);
