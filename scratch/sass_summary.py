@@ -2,7 +2,7 @@
 prefetches, bulk copies, mbarrier waits, packed fp32 math, byte permutes) -- from cuobjdump -sass of the built objects."""
 import collections, glob, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEYS = ["UTMALDG", "UTMAPF", "UBLKCP", "UBLKPF", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "PRMT", "LDS.128", "STS.128",
+KEYS = ["UTMALDG", "UTMAPF", "UTMASTG", "UBLKCP", "UBLKPF", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "PRMT", "LDS.128", "STS.128",
         "LDG.E.128", "REDUX", "CREDUX", "ATOMS", "BAR.SYNC"]
 out = ["SASS mnemonic counts per kernel (static instruction counts, cuobjdump -sass of pysilent_b200/build/*.o, sm_100a)", ""]
 for obj in sorted(glob.glob(os.path.join(ROOT, "pysilent_b200", "build", "*.o"))):
@@ -25,7 +25,7 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "pysilent_b200", "build", "*.o"))
                 if op == k or op.startswith(k + ".") or (k in ("LDS.128", "STS.128", "LDG.E.128") and op.startswith(k)):
                     counts[cur][k] += 1
     for name, c in counts.items():
-        if c["total"] < 200 and not any(c[k] for k in KEYS[:5]):
+        if c["total"] < 200 and not any(c[k] for k in KEYS[:6]):
             continue
         out.append("%s  [%s]" % (name, os.path.basename(obj)))
         out.append("    total %d; " % c["total"] + ", ".join("%s %d" % (k, c[k]) for k in KEYS if c[k]))
