@@ -163,7 +163,7 @@ def run_reference(args, rank):
                 "installable, the reference itself cannot run; cpu_baseline.reference_python times scipy's zoom as the "
                 "reference calls it",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------------------------
@@ -522,7 +522,7 @@ def run_ours(args, rank, local_rank, world):
         base["reference_python"] = {"C1": reference_python_sample(1, 5), "C3": reference_python_sample(3, 3)}
         base["C1_port"] = cpu_port_sample(3.0, 1)
         line["cpu_baseline"] = base
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -545,6 +545,9 @@ def structured_input_entry(pipe, dev, B, plan):
             "ms_per_step": ms, "frames_per_s_per_gpu": B / (ms * 1e-3)}
 
 
+RESULT_OUT = sys.stdout   # where the JSON line goes (main() saves the real stdout before redirecting fd 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -562,6 +565,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: file descriptor 1 is pointed at stderr for everything else that writes to it
+    # (NCCL prints its version banner there from native code), the JSON line goes to the saved descriptor
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
