@@ -81,6 +81,9 @@ silent_plan::~silent_plan()
     if (d_pair_words) cudaFree(d_pair_words);
     if (d_pair_htab) cudaFree(d_pair_htab);
     if (d_pair_ytab) cudaFree(d_pair_ytab);
+    if (frames_tex) cudaDestroyTextureObject(frames_tex);
+    if (ytab_tex) cudaDestroyTextureObject(ytab_tex);
+    if (htab_tex) cudaDestroyTextureObject(htab_tex);
 }
 
 extern "C" {

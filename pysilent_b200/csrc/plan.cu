@@ -212,6 +212,9 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
         if ((size_t)pl.th * pl.vpitch * 8 > 190 * 1024) plan->pair_ok = false;
     }
 
+    if (const char *e = std::getenv("SILENT_PYRAMID_TEX")) plan->pair_tex_enabled = std::atoi(e) != 0;   // A/B knobs
+    if (const char *e = std::getenv("SILENT_PYRAMID_TEXTAB")) plan->pair_tex_tables = std::atoi(e);
+
     if (L > 0) {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -295,6 +298,24 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_ytab, ytab.size() * sizeof(int32_t));
                 if (e == cudaSuccess)
                     e = cudaMemcpy(plan->d_pair_ytab, ytab.data(), ytab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+                if (e == cudaSuccess) {   // both tables as linear textures of int4 texels (a failure only disables the option)
+                    void *ptrs[2] = {plan->d_pair_ytab, plan->d_pair_htab};
+                    size_t bytes[2] = {ytab.size() * sizeof(int32_t), htab.size() * sizeof(int32_t)};
+                    cudaTextureObject_t *objs[2] = {&plan->ytab_tex, &plan->htab_tex};
+                    for (int i = 0; i < 2; ++i) {
+                        cudaResourceDesc rd = {};
+                        rd.resType = cudaResourceTypeLinear;
+                        rd.res.linear.devPtr = ptrs[i];
+                        rd.res.linear.desc = cudaCreateChannelDesc<int4>();
+                        rd.res.linear.sizeInBytes = bytes[i];
+                        cudaTextureDesc td = {};
+                        td.readMode = cudaReadModeElementType;
+                        if (cudaCreateTextureObject(objs[i], &rd, &td, nullptr) != cudaSuccess) {
+                            (void)cudaGetLastError();
+                            *objs[i] = 0;
+                        }
+                    }
+                }
                 if (e != cudaSuccess) {
                     delete plan;
                     return fail(SILENT_E_CUDA, "upload of pyramid tile spans failed: %s", cudaGetErrorString(e));

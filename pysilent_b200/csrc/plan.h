@@ -71,6 +71,12 @@ struct silent_plan {
     int *d_pair_words = nullptr;           // [L][kPairMaxTiles][4]: (word_lo, nwords, 2^32 / groups + 1, 0) per level and x tile
     int32_t *d_pair_htab = nullptr;        // [L][w][3][12]: phase-H tap offsets in the tile's column-sum row (6 ints) and weights (6 floats)
     int32_t *d_pair_ytab = nullptr;        // [L][h][12]: phase-V byte offsets of the six tap rows in a frame ([0] < 0: zero row) and weights
+    int pair_tex_tables = 2;               // bit 0 / 1: the phase-V / phase-H table entries take the texture path too
+    cudaTextureObject_t ytab_tex = 0, htab_tex = 0;   // d_pair_ytab / d_pair_htab as linear textures of int4 texels
+    bool pair_tex_enabled = true;          // phase V of pyramid_pair_kernel reads the frames through the texture path
+    cudaTextureObject_t frames_tex = 0;    // cached linear texture over the caller's frames (pyramid.cu)
+    const void *frames_tex_ptr = nullptr;
+    size_t frames_tex_bytes = 0;
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;

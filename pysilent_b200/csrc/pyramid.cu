@@ -131,6 +131,8 @@ constexpr int kVGroup = kPairVGroup;   // float2 slots per group of 16 byte-colu
 
 struct PairParams {
     const uint8_t *frames;
+    cudaTextureObject_t frames_tex;   // TEX variant: the same frames as a linear texture of 128-bit texels
+    cudaTextureObject_t ytab_tex, htab_tex;   // the two tables as textures of int4 texels
     f2 *xpair;
     const int4 *ytab;     // [L][h][3]: phase-V byte offsets of the six tap rows inside a frame + six weights (plan.cu)
     const int4 *words;    // [L][kPairMaxTiles]: (first 32-bit word of a frame row, word count, 2^32 / groups + 1, 0) per x tile
@@ -151,6 +153,14 @@ __device__ __forceinline__ float magic_byte(uint32_t word, uint32_t selector)
     return __uint_as_float(__byte_perm(word, 0x4B000000u, selector));
 }
 
+// TEX: phase V fetches the frame rows as 128-bit texels (tex1Dfetch, SASS TLD.LZ) instead of LDG.128. The kernel is
+// bound by the L1 data pipe of the LSU (86 % busy with LDG; a 512-byte LDG.128 costs 8 of its wavefronts -- the row loads
+// were 28 % of the kernel's total, the table loads another 14 %): the texture path returns its data through the TEX
+// pipe's own write-back and leaves the LSU pipe to the shared-memory traffic of both phases (measured: 0.262 -> 0.250 ms
+// with the rows, 0.245 ms with the phase-H table entries too; the phase-V table entries gain nothing -- their latency
+// sits in front of every task's row loads). Same bits either way.
+template <int TEX, bool TEXY, bool TEXH>   // TEX: how many of a task's 12 row loads take the texture path; TEXY / TEXH: the
+                                           // phase-V / phase-H table entries too
 __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair_kernel(const __grid_constant__ PairParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,6 +182,9 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     const uint8_t *frameB = (2 * q + 1 < P.B) ? frameA + P.frame_bytes : frameA;
     const int nq = span.y >> 2;
     const uint32_t magic = (uint32_t)span.z;
+    // texel (16-byte) index of this tile's first word in frames A and B (every term is a multiple of 16 bytes)
+    const int texA = (int)(((size_t)(2 * q) * P.frame_bytes + (size_t)span.x * 4) >> 4);
+    const int texB = (2 * q + 1 < P.B) ? texA + (int)(P.frame_bytes >> 4) : texA;
 
     // ---- the coarsest level is the first reader of a frame pair (finer levels then hit L2): ask L2 for the same tile of
     //      the NEXT pair now, one bulk prefetch per (tap row, frame), so that CTA finds its rows in L2 instead of HBM --
@@ -192,7 +205,13 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
     for (int t = tid; t < rows * nq; t += kPairThreads) {
         const int r = nq > 1 ? (int)__umulhi((uint32_t)t, magic) : t, qi = t - r * nq;
-        const int4 y0 = __ldg(ytab + 3 * r), y1 = __ldg(ytab + 3 * r + 1), y2 = __ldg(ytab + 3 * r + 2);
+        int4 y0, y1, y2;
+        if constexpr (TEXY) {
+            const int yt = (level * h + oy0 + r) * 3;
+            y0 = tex1Dfetch<int4>(P.ytab_tex, yt), y1 = tex1Dfetch<int4>(P.ytab_tex, yt + 1), y2 = tex1Dfetch<int4>(P.ytab_tex, yt + 2);
+        } else {
+            y0 = __ldg(ytab + 3 * r), y1 = __ldg(ytab + 3 * r + 1), y2 = __ldg(ytab + 3 * r + 2);
+        }
         f2 acc[16];
         if (y0.x < 0) {
 #pragma unroll
@@ -204,8 +223,10 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
             uint4 qa[kTaps], qb[kTaps];
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
-                qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + yoff[j]) + qi);
-                qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + yoff[j]) + qi);
+                if (2 * j < TEX) qa[j] = tex1Dfetch<uint4>(P.frames_tex, texA + (yoff[j] >> 4) + qi);
+                else qa[j] = __ldg(reinterpret_cast<const uint4 *>(frameA + yoff[j]) + qi);
+                if (2 * j + 1 < TEX) qb[j] = tex1Dfetch<uint4>(P.frames_tex, texB + (yoff[j] >> 4) + qi);
+                else qb[j] = __ldg(reinterpret_cast<const uint4 *>(frameB + yoff[j]) + qi);
             }
             // The first tap is a plain product: fma(w, v, +0) and w * v differ only when the product is -0 (a negative
             // weight on a zero byte), and a -0 column sum cannot change any output bit (phase H adds every term to +0).
@@ -241,8 +262,14 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
         const int c = item % 3;
         const int ox = bx * P.tile_w + item / 3;
         if (ox >= w) break;
-        const int4 *tab = P.htab + ((size_t)level * w + ox) * 9 + 3 * c;
-        const int4 t0 = __ldg(tab), t1 = __ldg(tab + 1), t2 = __ldg(tab + 2);
+        int4 t0, t1, t2;
+        if constexpr (TEXH) {
+            const int ht = (level * w + ox) * 9 + 3 * c;
+            t0 = tex1Dfetch<int4>(P.htab_tex, ht), t1 = tex1Dfetch<int4>(P.htab_tex, ht + 1), t2 = tex1Dfetch<int4>(P.htab_tex, ht + 2);
+        } else {
+            const int4 *tab = P.htab + ((size_t)level * w + ox) * 9 + 3 * c;
+            t0 = __ldg(tab), t1 = __ldg(tab + 1), t2 = __ldg(tab + 2);
+        }
         const int off[kTaps] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y};
         const float wv[kTaps] = {__int_as_float(t1.z), __int_as_float(t1.w), __int_as_float(t2.x),
                                  __int_as_float(t2.y), __int_as_float(t2.z), __int_as_float(t2.w)};
@@ -282,9 +309,44 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     if (pairs > 65535) return fail(SILENT_E_SHAPE, "at most 131070 frames per call");
     // per launch, not once per process: the attribute belongs to the CURRENT device's context, and one process may
     // drive several GPUs (one LineEndPipeline per camera thread and device)
-    SILENT_CUDA(cudaFuncSetAttribute(pyramid_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // frames as a texture of 128-bit texels (cached per plan: same pointer and size -> same object); the texel index is
+    // a 32-bit int and 1-D linear textures hold at most 2^27 texels
+    const size_t total_bytes = (size_t)batch * p.frame_h * p.frame_w * p.frame_c;
+    bool use_tex = plan->pair_tex_enabled && (total_bytes >> 4) < ((size_t)1 << 27);
+    cudaTextureObject_t tex = 0;
+    if (use_tex) {
+        silent_plan *mp = const_cast<silent_plan *>(plan);   // (the cache is plan-owned scratch, like the workspace)
+        if (mp->frames_tex == 0 || mp->frames_tex_ptr != frames_dev || mp->frames_tex_bytes != total_bytes) {
+            if (mp->frames_tex) cudaDestroyTextureObject(mp->frames_tex);
+            mp->frames_tex = 0;
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = const_cast<void *>(frames_dev);
+            rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+            rd.res.linear.sizeInBytes = total_bytes;
+            cudaTextureDesc td = {};
+            td.readMode = cudaReadModeElementType;
+            cudaTextureObject_t obj = 0;
+            if (cudaCreateTextureObject(&obj, &rd, &td, nullptr) == cudaSuccess) {
+                mp->frames_tex = obj, mp->frames_tex_ptr = frames_dev, mp->frames_tex_bytes = total_bytes;
+            } else {
+                (void)cudaGetLastError();
+                use_tex = false;   // (not an error: the LDG variant computes the same bits)
+            }
+        }
+        tex = mp->frames_tex;
+    }
+    auto kernel = pyramid_pair_kernel<0, false, false>;
+    if (use_tex) {
+        const bool ty = plan->ytab_tex != 0 && (plan->pair_tex_tables & 1), th = plan->htab_tex != 0 && (plan->pair_tex_tables & 2);
+        kernel = ty ? (th ? pyramid_pair_kernel<12, true, true> : pyramid_pair_kernel<12, true, false>)
+                    : (th ? pyramid_pair_kernel<12, false, true> : pyramid_pair_kernel<12, false, false>);
+    }
+    SILENT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PairParams P;
     P.frames = (const uint8_t *)frames_dev;
+    P.frames_tex = tex;
+    P.ytab_tex = plan->ytab_tex, P.htab_tex = plan->htab_tex;
     P.xpair = (f2 *)xpair_dev;
     P.ytab = reinterpret_cast<const int4 *>(plan->d_pair_ytab);
     P.words = reinterpret_cast<const int4 *>(plan->d_pair_words);
@@ -305,7 +367,7 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     }
     P.row_start[plan->levels] = tile_rows;
     if (tile_rows > 65535) return fail(SILENT_E_SHAPE, "too many tile rows for one launch (%d)", tile_rows);
-    SILENT_CUDA(launch_dependent(pyramid_pair_kernel, dim3(plan->pair[0].ntx, tile_rows, pairs), dim3(kPairThreads), smem,
+    SILENT_CUDA(launch_dependent(kernel, dim3(plan->pair[0].ntx, tile_rows, pairs), dim3(kPairThreads), smem,
                                  stream, P));
     SILENT_LAUNCH_CHECK("pyramid_pair_kernel");
     return SILENT_OK;

@@ -889,3 +889,23 @@ def test_pipeline_low_contrast_frames(c_oracle, default_filters):
         _check_stack(res, ref, None, "low contrast, %d grey levels" % levels_of_grey)
     host = pipe.run_host(frames)
     _check_stack(host, ref, None, "low contrast, host")
+
+
+@pytest.mark.parametrize("knobs", [{"SILENT_PYRAMID_TEX": "0"}, {"SILENT_PYRAMID_TEXTAB": "3"}, {"SILENT_PYRAMID_TEXTAB": "0"}])
+def test_pyramid_texture_and_ldg_variants_bit_identical(knobs, monkeypatch, c_oracle, default_filters):
+    """pyramid_pair_kernel fetches frame rows (and its phase-H table) through the texture path by default; the LDG
+    variant and the other table routings are the same arithmetic: bitwise equal to the default and to the oracle, on a
+    batch whose frames differ (texel indices of frame B) and an odd batch (frame B = frame A in the last pair)."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(2, i, 360, 640) for i in range(5)])
+    dev = torch.from_numpy(frames).cuda()
+    base = LineEndPipeline(zoom_ratio=1.5).run_frames(dev)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)   # read at plan creation: a fresh pipeline makes a fresh plan
+    other = LineEndPipeline(zoom_ratio=1.5).run_frames(dev)
+    for name in ("orient", "padded_line_end"):
+        a, b = getattr(base, name).cpu().numpy(), getattr(other, name).cpu().numpy()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), "%s differs with %s" % (name, knobs)
+    assert np.array_equal(base.points.cpu().numpy(), other.points.cpu().numpy())
+    _, ref = _oracle_pipeline(c_oracle, frames, (288, 192), 1.5, default_filters)
+    _check_stack(other, ref, None, "pyramid variant %s" % (knobs,))
