@@ -81,7 +81,8 @@ silent_plan::~silent_plan()
     if (d_pair_words) cudaFree(d_pair_words);
     if (d_pair_htab) cudaFree(d_pair_htab);
     if (d_pair_ytab) cudaFree(d_pair_ytab);
-    if (frames_tex) cudaDestroyTextureObject(frames_tex);
+    for (FrameTexture &ft : frame_textures)
+        if (ft.tex) cudaDestroyTextureObject(ft.tex);
     if (ytab_tex) cudaDestroyTextureObject(ytab_tex);
     if (htab_tex) cudaDestroyTextureObject(htab_tex);
 }

@@ -74,9 +74,15 @@ struct silent_plan {
     int pair_tex_tables = 2;               // bit 0 / 1: the phase-V / phase-H table entries take the texture path too
     cudaTextureObject_t ytab_tex = 0, htab_tex = 0;   // d_pair_ytab / d_pair_htab as linear textures of int4 texels
     bool pair_tex_enabled = true;          // phase V of pyramid_pair_kernel reads the frames through the texture path
-    cudaTextureObject_t frames_tex = 0;    // cached linear texture over the caller's frames (pyramid.cu)
-    const void *frames_tex_ptr = nullptr;
-    size_t frames_tex_bytes = 0;
+    // linear textures over the callers' frame buffers, keyed by (pointer, bytes). An object may still be read by a
+    // kernel in flight, so none is destroyed while the plan lives unless the table is full (then after a device
+    // synchronisation): the host-buffer path cycles through its <= kMaxChunks staging slices, callers through a few buffers
+    struct FrameTexture {
+        const void *ptr = nullptr;
+        size_t bytes = 0;
+        cudaTextureObject_t tex = 0;
+    };
+    std::vector<FrameTexture> frame_textures;
     void *d_tables = nullptr;
     int32_t *d_idx_y = nullptr, *d_idx_x = nullptr;
     float *d_w_y = nullptr, *d_w_x = nullptr;

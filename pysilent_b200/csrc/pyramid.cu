@@ -307,8 +307,6 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     const silent_params &p = plan->params;
     const int pairs = (batch + 1) / 2;
     if (pairs > 65535) return fail(SILENT_E_SHAPE, "at most 131070 frames per call");
-    // per launch, not once per process: the attribute belongs to the CURRENT device's context, and one process may
-    // drive several GPUs (one LineEndPipeline per camera thread and device)
     // frames as a texture of 128-bit texels (cached per plan: same pointer and size -> same object); the texel index is
     // a 32-bit int and 1-D linear textures hold at most 2^27 texels
     const size_t total_bytes = (size_t)batch * p.frame_h * p.frame_w * p.frame_c;
@@ -316,9 +314,15 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     cudaTextureObject_t tex = 0;
     if (use_tex) {
         silent_plan *mp = const_cast<silent_plan *>(plan);   // (the cache is plan-owned scratch, like the workspace)
-        if (mp->frames_tex == 0 || mp->frames_tex_ptr != frames_dev || mp->frames_tex_bytes != total_bytes) {
-            if (mp->frames_tex) cudaDestroyTextureObject(mp->frames_tex);
-            mp->frames_tex = 0;
+        for (const silent_plan::FrameTexture &ft : mp->frame_textures)
+            if (ft.ptr == frames_dev && ft.bytes == total_bytes) tex = ft.tex;
+        if (tex == 0) {
+            constexpr size_t kMaxFrameTextures = 64;
+            if (mp->frame_textures.size() >= kMaxFrameTextures) {   // rare: drop them all, once nothing can be reading them
+                SILENT_CUDA(cudaDeviceSynchronize());
+                for (silent_plan::FrameTexture &ft : mp->frame_textures) cudaDestroyTextureObject(ft.tex);
+                mp->frame_textures.clear();
+            }
             cudaResourceDesc rd = {};
             rd.resType = cudaResourceTypeLinear;
             rd.res.linear.devPtr = const_cast<void *>(frames_dev);
@@ -328,13 +332,15 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
             td.readMode = cudaReadModeElementType;
             cudaTextureObject_t obj = 0;
             if (cudaCreateTextureObject(&obj, &rd, &td, nullptr) == cudaSuccess) {
-                mp->frames_tex = obj, mp->frames_tex_ptr = frames_dev, mp->frames_tex_bytes = total_bytes;
+                silent_plan::FrameTexture ft;
+                ft.ptr = frames_dev, ft.bytes = total_bytes, ft.tex = obj;
+                mp->frame_textures.push_back(ft);
+                tex = obj;
             } else {
-                (void)cudaGetLastError();
-                use_tex = false;   // (not an error: the LDG variant computes the same bits)
+                (void)cudaGetLastError();   // e.g. a pointer below the texture alignment: the LDG variant computes the
+                use_tex = false;            // same bits
             }
         }
-        tex = mp->frames_tex;
     }
     auto kernel = pyramid_pair_kernel<0, false, false>;
     if (use_tex) {
@@ -342,6 +348,8 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
         kernel = ty ? (th ? pyramid_pair_kernel<12, true, true> : pyramid_pair_kernel<12, true, false>)
                     : (th ? pyramid_pair_kernel<12, false, true> : pyramid_pair_kernel<12, false, false>);
     }
+    // per launch, not once per process: the attribute belongs to the CURRENT device's context, and one process may
+    // drive several GPUs (one LineEndPipeline per camera thread and device)
     SILENT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     PairParams P;
     P.frames = (const uint8_t *)frames_dev;

@@ -909,3 +909,26 @@ def test_pyramid_texture_and_ldg_variants_bit_identical(knobs, monkeypatch, c_or
     assert np.array_equal(base.points.cpu().numpy(), other.points.cpu().numpy())
     _, ref = _oracle_pipeline(c_oracle, frames, (288, 192), 1.5, default_filters)
     _check_stack(other, ref, None, "pyramid variant %s" % (knobs,))
+
+
+def test_pyramid_texture_path_unaligned_frame_pointer(c_oracle, default_filters):
+    """Frames handed over as a slice of a larger device buffer: the pointer is 16-byte aligned (required) but not aligned
+    to the texture alignment (672000-byte frames). Whether the driver accepts the linear texture or the launch falls back
+    to the LDG variant, the results are the oracle's; many different slices cycle through the plan's texture table."""
+    from pysilent_b200 import LineEndPipeline
+    frames = np.stack([synthetic_frame(7, i, 2000, 112) for i in range(4)])
+    dev = torch.from_numpy(frames).cuda()
+    pipe = LineEndPipeline(zoom_ratio=1.5)
+    for lo, hi in ((1, 3), (1, 4), (2, 4), (0, 4)):
+        _, ref = _oracle_pipeline(c_oracle, frames[lo:hi], (288, 192), 1.5, default_filters)
+        _check_stack(pipe.run_frames(dev[lo:hi]), ref, None, "frames[%d:%d]" % (lo, hi))
+    big = torch.zeros(70 * 4 * 96 * 160 * 3 + 16, dtype=torch.uint8, device="cuda")
+    small = np.stack([synthetic_frame(3, i, 96, 160) for i in range(2)])
+    _, ref = _oracle_pipeline(c_oracle, small, (32, 24), 1.5, default_filters)
+    pipe2 = LineEndPipeline(output_size=(32, 24), zoom_ratio=1.5)
+    for i in range(70):   # more distinct buffers than the table holds: it is flushed (after a synchronisation) and refilled
+        view = big[16 + i * small.size: 16 + (i + 1) * small.size].view(small.shape)
+        view.copy_(torch.from_numpy(small))
+        res = pipe2.run_frames(view)
+        if i in (0, 1, 63, 64, 65, 69):
+            _check_stack(res, ref, None, "buffer %d" % i)
