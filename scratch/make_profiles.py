@@ -19,7 +19,12 @@ METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 
            'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
            'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
            'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
-           'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max']
+           'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max',
+           # the LSU's L1 data pipe (what bounds every kernel of the step) and what the TEX pipe carries beside it
+           'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+           'SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg',
+           'SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg',
+           'l1tex__t_output_wavefronts_pipe_tex_mem_texture.sum', 'l1tex__tex_writeback_active.sum']
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]

@@ -3,7 +3,7 @@ prefetches, bulk copies, mbarrier waits, packed fp32 math, byte permutes) -- fro
 import collections, glob, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = ["UTMALDG", "UTMAPF", "UTMASTG", "UBLKCP", "UBLKPF", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "PRMT", "LDS.128", "STS.128",
-        "LDG.E.128", "REDUX", "CREDUX", "ATOMS", "BAR.SYNC"]
+        "LDG.E.128", "TLD", "REDUX", "CREDUX", "ATOMS", "BAR.SYNC"]
 out = ["SASS mnemonic counts per kernel (static instruction counts, cuobjdump -sass of pysilent_b200/build/*.o, sm_100a)", ""]
 for obj in sorted(glob.glob(os.path.join(ROOT, "pysilent_b200", "build", "*.o"))):
     txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
