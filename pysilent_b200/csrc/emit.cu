@@ -37,7 +37,12 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int n_in)
 
 constexpr float kNegInf = -INFINITY;
 
-// grid (oh*ow, n); one CTA reduces one window of one level.
+// grid (oh*ow, n, row slices): a CTA reduces one slice of the rows of one window of one level (the windows of the
+// reference's max_pool span the WHOLE level, so one CTA per window walked 55 k pixels on its own: 62 us for a 1080p frame).
+// Warps take rows, lanes take columns: independent loads, no index division. The slices meet in `pooled` (preset to
+// 0xffffffff, which loses against every float below) through an order-independent NaN-propagating float maximum: signed
+// atomicMax for values >= +0, unsigned atomicMin for negative ones, and NaN (0x7fc00000, above every finite or infinite
+// pattern in both orders) through the signed atomicMax.
 __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict__ value, int h, int w, int region_h,
                                                          int region_w, PoolGeom g, float *__restrict__ pooled)
 {
@@ -45,26 +50,38 @@ __global__ void __launch_bounds__(256) window_max_kernel(const float *__restrict
     const int i = win / g.ow, j = win % g.ow;
     int ya = i * region_h - g.pt, yb = ya + h, xa = j * region_w - g.pl, xb = xa + w;
     ya = max(ya, 0), xa = max(xa, 0), yb = min(yb, h), xb = min(xb, w);
-    const int ww = xb - xa, count = (yb - ya) * ww;
+    const int per = ((yb - ya) + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int y0 = ya + (int)blockIdx.z * per, y1 = min(yb, y0 + per);
     const float *v = value + (size_t)n * h * w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float best = kNegInf;
-    int seen_nan = 0;
-    for (int t = threadIdx.x; t < count; t += blockDim.x) {
-        const float f = __ldg(v + (size_t)(ya + t / ww) * w + xa + t % ww);
-        if (f != f) seen_nan = 1;
-        else if (f > best) best = f;
+    int seen_nan = 0, seen_any = 0;
+    for (int y = y0 + warp; y < y1; y += 8) {
+        const float *row = v + (size_t)y * w;
+#pragma unroll 4
+        for (int x = xa + lane; x < xb; x += 32) {
+            const float f = __ldg(row + x);
+            seen_any = 1;
+            if (f != f) seen_nan = 1;
+            else if (f > best) best = f;
+        }
     }
     __shared__ float s_best[8];
-    __shared__ int s_nan[8];
+    __shared__ int s_nan[8], s_any[8];
     for (int o = 16; o > 0; o >>= 1) {
         best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));   // no NaN reaches here
         seen_nan |= __shfl_xor_sync(0xffffffffu, seen_nan, o);
+        seen_any |= __shfl_xor_sync(0xffffffffu, seen_any, o);
     }
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best, s_nan[threadIdx.x >> 5] = seen_nan;
+    if (lane == 0) s_best[warp] = best, s_nan[warp] = seen_nan, s_any[warp] = seen_any;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = fmaxf(best, s_best[k]), seen_nan |= s_nan[k];
-        pooled[(size_t)n * g.oh * g.ow + win] = seen_nan ? __int_as_float(0x7fc00000) : best;
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) best = fmaxf(best, s_best[k]), seen_nan |= s_nan[k], seen_any |= s_any[k];
+        if (!seen_any) return;   // an empty slice
+        int *dst = reinterpret_cast<int *>(pooled + (size_t)n * g.oh * g.ow + win);
+        if (seen_nan) atomicMax(dst, 0x7fc00000);
+        else if (!(__float_as_int(best) < 0)) atomicMax(dst, __float_as_int(best));
+        else atomicMin(reinterpret_cast<unsigned int *>(dst), __float_as_uint(best));
     }
 }
 
@@ -459,7 +476,9 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
         // the stack kernel already reduced the per-region maxima (ordered-int encoding == float bits, NaN = 0x7fc00000)
         pooled = reinterpret_cast<float *>(const_cast<int *>(fused_winmax));
     } else {
-        window_max_kernel<<<dim3(g.oh * g.ow, n), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
+        const int slices = std::max(1, std::min(h / 8, 16));   // row slices per window: enough CTAs for one frame's levels
+        SILENT_CUDA(cudaMemsetAsync(pooled, 0xff, (size_t)n * g.oh * g.ow * sizeof(float), stream));
+        window_max_kernel<<<dim3(g.oh * g.ow, n, slices), 256, 0, stream>>>(value, h, w, region_h, region_w, g, pooled);
         SILENT_LAUNCH_CHECK("window_max_kernel");
     }
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
