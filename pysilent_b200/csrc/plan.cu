@@ -280,8 +280,11 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                 if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_htab, htab.size() * sizeof(int32_t));
                 if (e == cudaSuccess)
                     e = cudaMemcpy(plan->d_pair_htab, htab.data(), htab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
-                // phase-V table: per (level, output row) the byte offsets of its six tap rows inside a frame and the six
-                // weights, three 128-bit loads per task (a row the reference leaves undefined has offset[0] = -1)
+                // phase-V table: per (level, output row) 12 words = (offset of tap row 0 in a frame or -1 for a row the
+                // reference leaves undefined, STEP, six weights, offsets of tap rows 1..4). When the six tap rows are
+                // consecutive frame rows (every row but the few whose taps are mirrored at the crop's edge) STEP is the
+                // frame's row pitch in bytes and a task needs the first TWO 128-bit words only; else STEP = -(offset of
+                // tap row 5) - 1 and the third word holds the other four offsets.
                 std::vector<int32_t> ytab((size_t)L * h * 12, 0);
                 const int64_t row_bytes = (int64_t)p->frame_w * p->frame_c;
                 for (int s = 0; s < L; ++s)
@@ -289,11 +292,16 @@ int silent_plan_create(const silent_params *p, silent_plan **out_plan)
                         const int32_t *ty = &plan->idx_y[((size_t)s * h + oy) * kTaps];
                         const float *gy = &plan->w_y[((size_t)s * h + oy) * kTaps];
                         int32_t *row = &ytab[((size_t)s * h + oy) * 12];
-                        for (int j = 0; j < kTaps; ++j) {
-                            row[j] = ty[0] >= 0 ? (int32_t)(ty[j] * row_bytes) : -1;
-                            const float wv = ty[0] >= 0 ? gy[j] : 0.0f;
-                            std::memcpy(&row[6 + j], &wv, 4);
+                        if (ty[0] < 0) {
+                            row[0] = -1, row[1] = (int32_t)row_bytes;   // (weights and offsets stay 0)
+                            continue;
                         }
+                        bool regular = true;
+                        for (int j = 1; j < kTaps; ++j) regular = regular && ty[j] == ty[0] + j;
+                        row[0] = (int32_t)(ty[0] * row_bytes);
+                        row[1] = regular ? (int32_t)row_bytes : -(int32_t)(ty[5] * row_bytes) - 1;
+                        std::memcpy(&row[2], gy, kTaps * sizeof(float));
+                        for (int j = 1; j <= 4; ++j) row[7 + j] = (int32_t)(ty[j] * row_bytes);
                     }
                 if (e == cudaSuccess) e = cudaMalloc(&plan->d_pair_ytab, ytab.size() * sizeof(int32_t));
                 if (e == cudaSuccess)

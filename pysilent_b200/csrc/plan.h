@@ -70,7 +70,7 @@ struct silent_plan {
     int pair_tile_w = 64;                  // output columns per tile of the frame-pair pyramid kernel (see plan.cu)
     int *d_pair_words = nullptr;           // [L][kPairMaxTiles][4]: (word_lo, nwords, 2^32 / groups + 1, 0) per level and x tile
     int32_t *d_pair_htab = nullptr;        // [L][w][3][12]: phase-H tap offsets in the tile's column-sum row (6 ints) and weights (6 floats)
-    int32_t *d_pair_ytab = nullptr;        // [L][h][12]: phase-V byte offsets of the six tap rows in a frame ([0] < 0: zero row) and weights
+    int32_t *d_pair_ytab = nullptr;        // [L][h][12]: phase-V table: first tap row's byte offset ([0] < 0: zero row), step, six weights, other offsets (plan.cu)
     int pair_tex_tables = 2;               // bit 0 / 1: the phase-V / phase-H table entries take the texture path too
     cudaTextureObject_t ytab_tex = 0, htab_tex = 0;   // d_pair_ytab / d_pair_htab as linear textures of int4 texels
     bool pair_tex_enabled = true;          // phase V of pyramid_pair_kernel reads the frames through the texture path

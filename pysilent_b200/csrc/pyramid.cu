@@ -134,7 +134,7 @@ struct PairParams {
     cudaTextureObject_t frames_tex;   // TEX variant: the same frames as a linear texture of 128-bit texels
     cudaTextureObject_t ytab_tex, htab_tex;   // the two tables as textures of int4 texels
     f2 *xpair;
-    const int4 *ytab;     // [L][h][3]: phase-V byte offsets of the six tap rows inside a frame + six weights (plan.cu)
+    const int4 *ytab;     // [L][h][3]: phase-V table (first tap row's byte offset, step, six weights | other offsets; plan.cu)
     const int4 *words;    // [L][kPairMaxTiles]: (first 32-bit word of a frame row, word count, 2^32 / groups + 1, 0) per x tile
     const int4 *htab;     // [L][w][3][3]: phase-H tap offsets in the tile's column-sum row + six weights (plan.cu)
     size_t frame_bytes;
@@ -189,11 +189,12 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     // ---- the coarsest level is the first reader of a frame pair (finer levels then hit L2): ask L2 for the same tile of
     //      the NEXT pair now, one bulk prefetch per (tap row, frame), so that CTA finds its rows in L2 instead of HBM --
     if (level == P.L - 1 && 2 * (q + 1) < P.B && nq > 0) {
-        const int32_t *yoff = reinterpret_cast<const int32_t *>(ytab);
+        const int32_t *yt = reinterpret_cast<const int32_t *>(ytab);
         for (int i = tid; i < 2 * rows * kTaps; i += kPairThreads) {
-            const int e = i >> 1, f = 2 + (i & 1), r = e / kTaps;
-            const int off = __ldg(yoff + 12 * r + (e - kTaps * r));
-            if (__ldg(yoff + 12 * r) >= 0 && 2 * q + f < P.B) {
+            const int e = i >> 1, f = 2 + (i & 1), r = e / kTaps, j = e - kTaps * r;
+            const int off0 = __ldg(yt + 12 * r), step = __ldg(yt + 12 * r + 1);
+            const int off = step > 0 ? off0 + j * step : j == 0 ? off0 : j == 5 ? -step - 1 : __ldg(yt + 12 * r + 7 + j);
+            if (off0 >= 0 && 2 * q + f < P.B) {
                 const uint8_t *src = frameA + (size_t)f * P.frame_bytes + off;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(span.y * 4) : "memory");
             }
@@ -205,21 +206,28 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     const f2 bias = make_float2(-8388608.0f, -8388608.0f);
     for (int t = tid; t < rows * nq; t += kPairThreads) {
         const int r = nq > 1 ? (int)__umulhi((uint32_t)t, magic) : t, qi = t - r * nq;
-        int4 y0, y1, y2;
-        if constexpr (TEXY) {
-            const int yt = (level * h + oy0 + r) * 3;
-            y0 = tex1Dfetch<int4>(P.ytab_tex, yt), y1 = tex1Dfetch<int4>(P.ytab_tex, yt + 1), y2 = tex1Dfetch<int4>(P.ytab_tex, yt + 2);
-        } else {
-            y0 = __ldg(ytab + 3 * r), y1 = __ldg(ytab + 3 * r + 1), y2 = __ldg(ytab + 3 * r + 2);
-        }
+        // the row's table entry: two 128-bit words (first offset, step, six weights); a third one only for the few rows
+        // whose tap rows are not consecutive (mirrored at the crop's edge)
+        auto ytab_word = [&](int k) {
+            if constexpr (TEXY) return tex1Dfetch<int4>(P.ytab_tex, (level * h + oy0 + r) * 3 + k);
+            else return __ldg(ytab + 3 * r + k);
+        };
+        const int4 y0 = ytab_word(0), y1 = ytab_word(1);
         f2 acc[16];
         if (y0.x < 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) acc[k] = make_float2(0.0f, 0.0f);
         } else {
-            const int yoff[kTaps] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y};
-            const float wyv[kTaps] = {__int_as_float(y1.z), __int_as_float(y1.w), __int_as_float(y2.x),
-                                      __int_as_float(y2.y), __int_as_float(y2.z), __int_as_float(y2.w)};
+            int yoff[kTaps];
+            if (y0.y > 0) {
+#pragma unroll
+                for (int j = 0; j < kTaps; ++j) yoff[j] = y0.x + j * y0.y;
+            } else {
+                const int4 y2 = ytab_word(2);
+                yoff[0] = y0.x, yoff[1] = y2.x, yoff[2] = y2.y, yoff[3] = y2.z, yoff[4] = y2.w, yoff[5] = -y0.y - 1;
+            }
+            const float wyv[kTaps] = {__int_as_float(y0.z), __int_as_float(y0.w), __int_as_float(y1.x),
+                                      __int_as_float(y1.y), __int_as_float(y1.z), __int_as_float(y1.w)};
             uint4 qa[kTaps], qb[kTaps];
 #pragma unroll
             for (int j = 0; j < kTaps; ++j) {
