@@ -142,7 +142,7 @@ static TileMaxima tile_maxima(const silent_plan *plan)
 // even on the frame-pair path (pairs never straddle a chunk).
 static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, const void *frames_dev, int frame0, int nb,
                             float *pyramid_dev, float *orient_dev, float *line_end_dev, const WindowGeom *geo,
-                            cudaStream_t s)
+                            cudaStream_t s, const PairClear *also_clear = nullptr)
 {
     Workspace &ws = plan->ws;
     const bool pair_path = pyramid_pair_supported(plan);
@@ -150,8 +150,19 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
     const size_t img0 = (size_t)frame0 * plan->levels;
     const int n = nb * plan->levels;
     const unsigned char *frames = (const unsigned char *)frames_dev + frame_bytes(plan) * frame0;
-    int rc = stack_clear_flags(ws.d_stack, n, plan->h, plan->w, s);   // ahead of the kernels: no memset between launches
-    if (rc != SILENT_OK) return rc;
+    // stack_b's tile flags must be zero before it runs: the frame-pair pyramid kernel clears them on its way (and what
+    // the caller adds in also_clear), so that no memset sits between the previous step's last kernel and this launch;
+    // without that kernel a memset ahead of the launches does it
+    int rc = SILENT_OK;
+    PairClear clear;
+    if (pair_path) {
+        stack_flag_region(ws.d_stack, n, plan->h, plan->w, &clear.a, &clear.a_bytes);
+        if (also_clear) clear.b = also_clear->b, clear.b_bytes = also_clear->b_bytes;
+    } else {
+        rc = stack_clear_flags(ws.d_stack, n, plan->h, plan->w, s);
+        if (rc != SILENT_OK) return rc;
+        if (also_clear && also_clear->b) SILENT_CUDA(cudaMemsetAsync(also_clear->b, 0, also_clear->b_bytes, s));
+    }
     // Fast path: the frame-pair pyramid kernel feeds the stack in its own pair-interleaved layout. The NHWC pyramid is
     // only materialised when the caller asks for it (pyramid_dev) or the plan does not qualify (float frames, ...).
     {
@@ -162,7 +173,7 @@ static int run_stack_stages(silent_plan *plan, const silent_stack_weights *W, co
             if (rc != SILENT_OK) return rc;
         }
         if (pair_path) {
-            rc = pyramid_pair_build(plan, frames, nb, ws.d_pyramid, s);
+            rc = pyramid_pair_build(plan, frames, nb, ws.d_pyramid, s, &clear);
             if (rc != SILENT_OK) return rc;
         }
     }
@@ -205,9 +216,10 @@ int silent_pipeline_run(silent_plan *plan, const silent_stack_weights *weights_h
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[0], s));
     WindowGeom geo;
     const bool fuse_windows = count_dev && window_geometry(plan->h, plan->w, plan->h / 2, plan->w / 2, &geo);
-    if (fuse_windows) SILENT_CUDA(cudaMemsetAsync(ws.d_winmax, 0, (size_t)n * geo.count * sizeof(int), s));
+    PairClear winmax_clear;   // the region maxima start at 0: cleared together with the tile flags (see run_stack_stages)
+    if (fuse_windows) winmax_clear.b = ws.d_winmax, winmax_clear.b_bytes = (size_t)n * geo.count * sizeof(int);
     rc = run_stack_stages(plan, weights_host, frames_dev, 0, batch, pyramid_dev, orient_dev, line_end_dev,
-                          fuse_windows ? &geo : nullptr, s);
+                          fuse_windows ? &geo : nullptr, s, &winmax_clear);
     if (rc != SILENT_OK) return rc;
     if (timing) SILENT_CUDA(cudaEventRecord(plan->ev[2], s));
     if (count_dev) {

@@ -139,6 +139,9 @@ struct PairParams {
     const int4 *htab;     // [L][w][3][3]: phase-H tap offsets in the tile's column-sum row + six weights (plan.cu)
     size_t frame_bytes;
     int h, w, L, B, tile_w;
+    uint4 *clear_a;       // zeroed by the first CTA of every pair (PairClear, stack.h): n16 128-bit words ...
+    uint32_t *clear_b;    // ... and n32 32-bit words
+    unsigned clear_n16, clear_n32;
     // ONE launch covers every level: blockIdx.x is the x tile, blockIdx.y enumerates the tile rows of a frame pair with
     // the COARSEST level first (it pulls the whole frame through L2; the finer levels, whose crops are subsets, then hit
     // L2), blockIdx.z the pair.
@@ -168,6 +171,11 @@ __global__ void __launch_bounds__(kPairThreads, 768 / kPairThreads) pyramid_pair
     pdl_enter();
 
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {   // (after the wait: the previous step's kernels have read these buffers)
+        const unsigned stride = gridDim.z * kPairThreads;
+        for (unsigned i = blockIdx.z * kPairThreads + tid; i < P.clear_n16; i += stride) P.clear_a[i] = make_uint4(0, 0, 0, 0);
+        for (unsigned i = blockIdx.z * kPairThreads + tid; i < P.clear_n32; i += stride) P.clear_b[i] = 0u;
+    }
     int k = 0;
     while (k + 1 < P.L && (int)blockIdx.y >= P.row_start[k + 1]) ++k;
     const int level = P.L - 1 - k, bx = blockIdx.x, by = blockIdx.y - P.row_start[k], q = blockIdx.z;
@@ -308,7 +316,8 @@ size_t pyramid_pair_bytes(const silent_plan *plan, int batch)
     return (size_t)((batch + 1) / 2) * plan->levels * 3 * plan->h * plan->w * sizeof(f2);
 }
 
-int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream)
+int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream,
+                       const PairClear *clear)
 {
     if (!pyramid_pair_supported(plan)) return fail(SILENT_E_SHAPE, "frame-pair pyramid kernel does not support this plan");
     if (((uintptr_t)frames_dev & 15) != 0) return fail(SILENT_E_INVAL, "frames must be 16-byte aligned");
@@ -370,6 +379,8 @@ int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batc
     P.frame_bytes = (size_t)p.frame_h * p.frame_w * p.frame_c;
     P.h = plan->h, P.w = plan->w, P.L = plan->levels, P.B = batch;
     P.tile_w = plan->pair_tile_w;
+    P.clear_a = clear ? (uint4 *)clear->a : nullptr, P.clear_n16 = clear && clear->a ? (unsigned)(clear->a_bytes / 16) : 0u;
+    P.clear_b = clear ? (uint32_t *)clear->b : nullptr, P.clear_n32 = clear && clear->b ? (unsigned)(clear->b_bytes / 4) : 0u;
     size_t smem = 0;
     int tile_rows = 0;
     for (int k = 0; k < plan->levels; ++k) {   // coarsest level first

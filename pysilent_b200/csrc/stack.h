@@ -19,6 +19,8 @@ int stack_fused(const void *pyr, int n, int h, int w, int pair_levels, const sil
                 int *winmax, int *tilemax, cudaStream_t stream, cudaEvent_t between_kernels = nullptr,
                 bool flags_clean = false);
 int stack_clear_flags(void *workspace, int n, int h, int w, cudaStream_t stream);
+// the region stack_clear_flags zeroes (256-byte aligned, a multiple of 256 bytes): the pipeline lets the pyramid kernel clear it
+void stack_flag_region(void *workspace, int n, int h, int w, void **ptr, size_t *bytes);
 // tile grid of stack_b_kernel; tilemax is int [n][nty][ntx] (ordered-int maxima of gray per tile, NaN = 0x7fc00000)
 void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx);
 struct TileMaxima {
@@ -34,7 +36,17 @@ int stack_bank(const void *xpair, int n, int h, int w, int pair_levels, const si
 int pyramid_build(const silent_plan *plan, const void *frames_dev, int batch, float *pyramid_dev, cudaStream_t stream);
 bool pyramid_pair_supported(const silent_plan *plan);
 size_t pyramid_pair_bytes(const silent_plan *plan, int batch);
-int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream);
+// Buffers the frame-pair pyramid kernel zeroes on its way (consumed by the kernels AFTER it: stack_b's tile flags and
+// region maxima): a memset in front of the pyramid launch would sit between the previous step's last kernel and this one
+// as a stream operation of its own. a: 16-byte aligned, bytes a multiple of 16; b: 4-byte words.
+struct PairClear {
+    void *a = nullptr;
+    size_t a_bytes = 0;
+    void *b = nullptr;
+    size_t b_bytes = 0;
+};
+int pyramid_pair_build(const silent_plan *plan, const void *frames_dev, int batch, void *xpair_dev, cudaStream_t stream,
+                       const PairClear *clear = nullptr);
 
 // emit.cu
 bool window_geometry(int h, int w, int region_h, int region_w, WindowGeom *geo);

@@ -1935,6 +1935,13 @@ void stack_tile_grid(int h, int w, int *tile_h, int *tile_w, int *nty, int *ntx)
 // winmax: optional int[n * windows] (zeroed by the caller) receiving the per-region maxima of gray; geometry in *geo.
 // Zeroes the tile flags (and the counter in front of them) stack_fused will use for n images; the pipeline calls this
 // ahead of the pyramid launch and then passes flags_clean = true.
+void stack_flag_region(void *workspace, int n, int h, int w, void **ptr, size_t *bytes)
+{
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    *ptr = base + stack_plane_bytes(n, h, w);
+    *bytes = stack_flag_bytes(n, h, w);
+}
+
 int stack_clear_flags(void *workspace, int n, int h, int w, cudaStream_t stream)
 {
     unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
