@@ -212,9 +212,12 @@ __device__ __forceinline__ bool tile_is_candidate(const TileMaxima &tm, const in
     return cand;
 }
 
+constexpr int kEmitCompact = 64;   // a level with at most this many hits hands their coordinates to emit_write_kernel
+
 __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
                                                          const float *__restrict__ pooled, TileMaxima tm,
-                                                         int *__restrict__ row_offset, int *__restrict__ level_total)
+                                                         int *__restrict__ row_offset, int *__restrict__ level_total,
+                                                         int *__restrict__ level_hits, int *__restrict__ level_compact)
 {
     pdl_enter();
     __shared__ int s_rows[kEmitMaxRows];
@@ -236,7 +239,11 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
     // are flagged (a loop per tile cost one round trip per flagged tile)
     __shared__ int s_list[kEmitMaxTiles];
     __shared__ int s_nflag;
-    if (tid == 0) s_nflag = 0;
+    // The hits themselves, (y << 16 | x), while there are at most kEmitCompact of them: sorted below and left for
+    // emit_write_kernel, which then needs neither the tile flags nor a second look at the pixels (two memory round trips)
+    __shared__ int s_hit[kEmitCompact], s_nhit;
+    const bool keep_hits = level_hits && w <= 65535;
+    if (tid == 0) s_nflag = 0, s_nhit = 0;
     __syncthreads();
     for (int t = tid; t < ntiles; t += 256)
         if (s_flag[t]) s_list[atomicAdd(&s_nflag, 1)] = t;
@@ -275,7 +282,13 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
             int hits = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (xs[u] + e < xe[u]) hits += f[e] >= __ldg(pool_row + nearest_src(xs[u] + e, g.sx, g.ow));
+                if (xs[u] + e < xe[u] && f[e] >= __ldg(pool_row + nearest_src(xs[u] + e, g.sx, g.ow))) {
+                    ++hits;
+                    if (keep_hits) {
+                        const int at = atomicAdd(&s_nhit, 1);
+                        if (at < kEmitCompact) s_hit[at] = (ys[u] << 16) | (xs[u] + e);
+                    }
+                }
             if (hits) atomicAdd(&s_rows[ys[u]], hits);
         }
     }
@@ -298,6 +311,17 @@ __global__ void __launch_bounds__(256) emit_count_kernel(const float *__restrict
         __syncthreads();
     }
     if (tid == 0) level_total[n] = s_carry;
+    if (level_compact) {   // (s_nhit is final since the barrier behind the scan loop)
+        const int cnt = s_nhit;
+        const bool compact = keep_hits && cnt <= kEmitCompact;
+        if (tid == 0) level_compact[n] = compact ? 1 : 0;
+        if (compact && tid < cnt) {   // rank sort: the keys are distinct, row-major order = key order
+            const int mine = s_hit[tid];
+            int rank = 0;
+            for (int k = 0; k < cnt; ++k) rank += s_hit[k] < mine;
+            level_hits[(size_t)n * kEmitCompact + rank] = mine;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict__ value, int h, int w, PoolGeom g,
@@ -305,12 +329,34 @@ __global__ void __launch_bounds__(256) emit_write_kernel(const float *__restrict
                                                          const int *__restrict__ row_offset,
                                                          const int *__restrict__ level_total, int levels,
                                                          long long *__restrict__ points, long long capacity,
-                                                         long long *__restrict__ total)
+                                                         long long *__restrict__ total, const int *__restrict__ level_hits,
+                                                         const int *__restrict__ level_compact)
 {
     pdl_enter();
     __shared__ long long s_sum[8];
     const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool last = n == levels - 1;
+    if (level_compact && __ldg(level_compact + n)) {
+        // emit_count_kernel left this level's (few) hits sorted: the totals of the levels before, the own count and the
+        // hit list are independent loads, one memory round trip, then the rows are written
+        const int cnt = __ldg(level_total + n);
+        const int key = tid < cnt ? __ldg(level_hits + (size_t)n * kEmitCompact + tid) : 0;
+        if (cnt == 0 && !last) return;
+        long long part = 0;
+        for (int k = tid; k < n; k += 256) part += __ldg(level_total + k);
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_sum[warp] = part;
+        __syncthreads();
+        long long base = 0;
+        for (int k = 0; k < 8; ++k) base += s_sum[k];
+        if (last && tid == 0) *total = base + cnt;
+        const long long at = base + tid;
+        if (tid < cnt && at < capacity) {
+            reinterpret_cast<longlong2 *>(points)[at * 2] = make_longlong2(n, key >> 16);
+            reinterpret_cast<longlong2 *>(points)[at * 2 + 1] = make_longlong2(key & 0xffff, 0);
+        }
+        return;
+    }
     // points of the levels before this one (the last level also publishes the grand total); these loads and the row
     // flags below are independent, so they share one memory round trip
     long long sum = 0;
@@ -484,12 +530,17 @@ int max_value_indices_region(const float *value, int n, int h, int w, int region
     if ((long long)h * w >= (1 << 30)) return fail(SILENT_E_SHAPE, "levels of 2^30 pixels or more are not supported");
     if (tiles && tiles->data && tiles->nty * tiles->ntx <= kEmitMaxTiles && h <= kEmitMaxRows) {
         // fused path: one CTA per level, only the tiles that can hold a hit are scanned
+        // the compact hit lists live in the workspace's window-maxima area when the stack kernel delivered the maxima
+        // (fused_winmax: that area is unused then), the per-level "compact" marks in the reserved words before level_total
+        int *level_hits = fused_winmax ? (int *)workspace : nullptr;
+        int *level_compact = fused_winmax ? (int *)((char *)level_total - align_up((size_t)n * sizeof(long long), 256)) : nullptr;
         SILENT_CUDA(launch_dependent(emit_count_kernel, dim3(n), dim3(256), 0, stream, value, h, w, g, (const float *)pooled,
-                                     *tiles, row_offset, level_total));
+                                     *tiles, row_offset, level_total, level_hits, level_compact));
         SILENT_LAUNCH_CHECK("emit_count_kernel");
         SILENT_CUDA(launch_dependent(emit_write_kernel, dim3(n), dim3(256), 0, stream, value, h, w, g, (const float *)pooled,
                                      *tiles, (const int *)row_offset, (const int *)level_total, n, (long long *)points,
-                                     (long long)capacity, (long long *)count));
+                                     (long long)capacity, (long long *)count, (const int *)level_hits,
+                                     (const int *)level_compact));
         SILENT_LAUNCH_CHECK("emit_write_kernel");
         return SILENT_OK;
     }
