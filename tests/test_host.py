@@ -111,3 +111,19 @@ def test_point_gather_two_ranks_gloo(tmp_path):
         assert np.array_equal(got, want)
     key = (want[:, 0] * 192 + want[:, 1]) * 288 + want[:, 2]
     assert (np.diff(key) >= 0).all()          # global order = frame-major, then the reference's row-major order
+
+
+def test_bench_cpu_arm_runs_on_worker_processes():
+    """bench.py's CPU arm (`--impl reference`, `cpu_baseline`): one spawned worker process per core runs the oracle port;
+    a round of two workers on the small C1 frames returns two finished frames, and a worker's result equals the parent's."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    port = bench.CpuPort(config=1, threads=2)
+    try:
+        assert port.round() == 2
+        mine = port.one(0)
+        theirs = list(port.pool.map(bench._cpu_worker_one, [0]))[0]
+        assert mine == theirs and mine >= 0
+    finally:
+        port.close()
