@@ -39,7 +39,7 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 // ---- programmatic dependent launch: the kernels of one pipeline step are launched with the stream-serialisation
 //      attribute, so a kernel's CTAs are scheduled while its predecessor drains and only its FIRST instruction waits for
-//      the predecessor's memory (no launch gap between the step's 7 kernels; matters most at batch 1). A kernel that is
+//      the predecessor's memory (no launch gap between the step's 6 kernels; matters most at batch 1). A kernel that is
 //      launched without the attribute passes both instructions at once.
 __device__ __forceinline__ void pdl_enter()
 {

@@ -16,7 +16,11 @@
 //                        planar layout xpair[pair][c][y][x] = (frame A, frame B) that stack_a_kernel loads verbatim.
 //                        One launch covers every level, coarsest first (it pulls a frame pair through L2 once; finer
 //                        levels re-read their crops from L2) and bulk-prefetches the next pair's rows into L2. Tile
-//                        width (72 columns for 288-wide levels) and height are chosen per plan (plan.cu).
+//                        width (72 columns for 288-wide levels) and height are chosen per plan (plan.cu). The frame
+//                        words and the phase-H table entries arrive through the TEXTURE path (tex1Dfetch on linear
+//                        textures, SASS TLD.LZ): the kernel is bound by the LSU's L1 data pipe, which the texture
+//                        unit's own write-back bypasses. The first CTA of every pair also zeroes the buffers that the
+//                        kernels AFTER this one expect clean (PairClear), so the step has no memset of its own.
 #include <algorithm>
 
 #include "plan.h"
